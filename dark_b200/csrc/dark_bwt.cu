@@ -1,0 +1,632 @@
+// dark_bwt.cu — context, round driver and C ABI (include/dark_bwt.h) of the B200-native forward BWT.
+//
+// Host-side control flow of one block (replaces saca::Constructor::compute + TransformIterator,
+// /root/reference/src/saca.rs:368-378 and src/block/dc.rs:45-50):
+//
+//   alphabet scan -> initial keys (K symbols per 64-bit key) -> radix sort -> re-rank/compact
+//   while (unsettled suffixes remain):  keys (rank[i], rank[i+h]) -> radix sort -> re-rank/compact;  h *= 2
+//   BWT gather + origin
+//
+// All device memory is carved from one arena allocated at create (Constructor::new allocates its
+// arena up front too, saca.rs:351-360); the forward calls allocate nothing.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/dark_bwt.h"
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "suffix_kernels.cuh"
+
+using namespace dark;
+
+namespace {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr int kInitThreads = 256;
+constexpr int kInitItems = 16;
+constexpr int kBuildThreads = 256;
+constexpr int kBuildItems = 8;
+constexpr int kMaxCounters = 1024;
+constexpr int kMaxEvents = 16 + 10 * DARK_BWT_MAX_ROUNDS;
+
+enum Phase { PH_INIT = 0, PH_SORT, PH_PASS, PH_KEYBUILD, PH_RERANK, PH_EMIT, PH_COUNT };
+
+struct Mailbox {  // pinned host memory the device results are copied into
+    u32 sigma;
+    u32 count;
+    u32 trivial[kMaxPasses];
+    u64 origin;
+    unsigned long long bad;
+};
+
+struct DeviceScalars {  // mirrors Mailbox on the device
+    u32 sigma;
+    u32 count;
+    u32 trivial[kMaxPasses];
+    u64 origin;
+    unsigned long long bad;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int bit_length(u64 x) {
+    int b = 0;
+    while (x) {
+        ++b;
+        x >>= 1;
+    }
+    return b;
+}
+
+}  // namespace
+
+struct dark_bwt_ctx {
+    int device = 0;
+    u64 capacity = 0;
+    u32 flags = 0;
+    cudaStream_t stream = nullptr;
+
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    u64* keys[2] = {nullptr, nullptr};
+    u32* ids[2] = {nullptr, nullptr};
+    u32* ranks = nullptr;
+    u32* isa = nullptr;
+    u32* sa = nullptr;
+    u8* d_text = nullptr;  // host-entry staging
+    u8* d_bwt = nullptr;
+    u32* hist = nullptr;
+    u32* present = nullptr;
+    u8* lut = nullptr;
+    DeviceScalars* scalars = nullptr;
+    void* sort_status = nullptr;
+    size_t sort_status_bytes = 0;
+    u32* counters = nullptr;
+    u32* scan_flag = nullptr;
+    uint4* scan_agg = nullptr;
+    uint4* scan_incl = nullptr;
+    size_t scan_tiles = 0;
+
+    Mailbox* mail = nullptr;
+    u32* reuse_words = nullptr;
+    u64 reuse_count = 0;
+
+    cudaEvent_t events[kMaxEvents];
+    int n_events = 0;
+    struct Span {
+        int phase, e0, e1;
+    };
+    std::vector<Span> spans;
+    int next_counter = 0;
+    u32 launches = 0;
+    char err[320] = {0};
+
+    int fail_cuda(cudaError_t e, const char* what, int line) {
+        snprintf(err, sizeof(err), "CUDA error %d (%s) at dark_bwt.cu:%d: %s", (int)e, cudaGetErrorString(e), line, what);
+        return DARK_BWT_E_CUDA;
+    }
+    int fail_internal(const char* what) {
+        snprintf(err, sizeof(err), "internal error: %s", what);
+        return DARK_BWT_E_INTERNAL;
+    }
+};
+
+#define CK(call)                                                              \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return ctx->fail_cuda(e__, #call, __LINE__); \
+    } while (0)
+#define LAUNCHED()            \
+    do {                      \
+        ctx->launches += 1;   \
+        CK(cudaGetLastError()); \
+    } while (0)
+
+namespace {
+
+int span_begin(dark_bwt_ctx* ctx, int phase) {
+    if (ctx->n_events + 2 > kMaxEvents - 4) return -1;  // the last events are reserved for the entry points
+    int e0 = ctx->n_events++;
+    cudaEventRecord(ctx->events[e0], ctx->stream);
+    ctx->spans.push_back({phase, e0, -1});
+    return (int)ctx->spans.size() - 1;
+}
+void span_end(dark_bwt_ctx* ctx, int span) {
+    if (span < 0) return;
+    int e1 = ctx->n_events++;
+    cudaEventRecord(ctx->events[e1], ctx->stream);
+    ctx->spans[span].e1 = e1;
+}
+
+template <typename K>
+int set_smem(dark_bwt_ctx* ctx, K kernel, size_t bytes) {
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+int next_counter(dark_bwt_ctx* ctx, u32** out) {
+    if (ctx->next_counter >= kMaxCounters) return ctx->fail_internal("tile counters exhausted");
+    *out = ctx->counters + ctx->next_counter++;
+    return 0;
+}
+
+// One onesweep pass over m pairs: buffers[cur] -> buffers[cur^1].
+int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
+                const u32* digit_base) {
+    typedef OnesweepSmem<kSortThreads, kSortItems> Smem;
+    const u32 tiles = (u32)ceil_div(m, kSortTile);
+    u32* counter = nullptr;
+    if (int rc = next_counter(ctx, &counter)) return rc;
+    // 32-bit status words hold prefixes below 2^30; larger sorts (2 GiB blocks) use 64-bit words.
+    // DARK_BWT_FORCE_U64_STATUS=1 exercises the wide path on small inputs (tests).
+    static const bool force64 = getenv("DARK_BWT_FORCE_U64_STATUS") != nullptr;
+    if (m < (1u << 30) && !force64) {
+        const size_t bytes = (size_t)tiles * kRadix * sizeof(u32);
+        if (bytes > ctx->sort_status_bytes) return ctx->fail_internal("sort status buffer too small");
+        CK(cudaMemsetAsync(ctx->sort_status, 0, bytes, ctx->stream));
+        k_onesweep_pass<kSortThreads, kSortItems, u32><<<tiles, kSortThreads, sizeof(Smem), ctx->stream>>>(
+            kin, vin, kout, vout, m, shift, digit_base, (u32*)ctx->sort_status, counter);
+    } else {
+        const size_t bytes = (size_t)tiles * kRadix * sizeof(u64);
+        if (bytes > ctx->sort_status_bytes) return ctx->fail_internal("sort status buffer too small");
+        CK(cudaMemsetAsync(ctx->sort_status, 0, bytes, ctx->stream));
+        k_onesweep_pass<kSortThreads, kSortItems, u64><<<tiles, kSortThreads, sizeof(Smem), ctx->stream>>>(
+            kin, vin, kout, vout, m, shift, digit_base, (u64*)ctx->sort_status, counter);
+    }
+    LAUNCHED();
+    return 0;
+}
+
+// Sort passes for a histogram that is already in ctx->hist (counts).  `cur` is the index of the
+// (keys, ids) pair holding the input; returns the index holding the output through *cur_out.
+int run_sort(dark_bwt_ctx* ctx, u64* const keys[2], u32* const vals[2], int cur, u32 m, int begin_bit, int num_passes,
+             int* cur_out, dark_bwt_stats* st, int round) {
+    k_scan_hist<<<num_passes, kRadix, 0, ctx->stream>>>(ctx->hist, m, ctx->scalars->trivial);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(ctx->mail->trivial, ctx->scalars->trivial, sizeof(u32) * kMaxPasses, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int sp = span_begin(ctx, PH_PASS);
+    for (int p = 0; p < num_passes; ++p) {
+        if (ctx->mail->trivial[p]) continue;  // every key has the same digit: the pass is the identity
+        if (int rc = launch_pass(ctx, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], m, begin_bit + p * kRadixBits,
+                                 ctx->hist + p * kRadix))
+            return rc;
+        cur ^= 1;
+        if (st) {
+            st->sort_passes += 1;
+            st->sorted_elements += m;
+            if (round < DARK_BWT_MAX_ROUNDS) st->passes[round] += 1;
+        }
+    }
+    span_end(ctx, sp);
+    *cur_out = cur;
+    return 0;
+}
+
+template <bool ROUND0>
+int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32 n, int K, int kb, u32* sa,
+                  u32* out_ids) {
+    const u32 tiles = (u32)ceil_div(m, kScanTile);
+    if (tiles > ctx->scan_tiles) return ctx->fail_internal("scan tile state too small");
+    u32* counter = nullptr;
+    if (int rc = next_counter(ctx, &counter)) return rc;
+    CK(cudaMemsetAsync(ctx->scan_flag, 0, sizeof(u32) * tiles, ctx->stream));
+    ScanTileState ts{ctx->scan_flag, ctx->scan_agg, ctx->scan_incl};
+    k_rerank<kScanThreads, kScanItems, ROUND0><<<tiles, kScanThreads, 0, ctx->stream>>>(
+        keys, ids, m, n, K, kb, ctx->isa, sa, out_ids, ctx->ranks, ts, counter, &ctx->scalars->count);
+    LAUNCHED();
+    return 0;
+}
+
+int fetch_count(dark_bwt_ctx* ctx, u32* out) {
+    CK(cudaMemcpyAsync(&ctx->mail->count, &ctx->scalars->count, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = ctx->mail->count;
+    return 0;
+}
+
+int emit(dark_bwt_ctx* ctx, const u8* d_text, u32 n, const u32* d_sa, u8* d_bwt) {
+    const u32 blocks = (u32)ceil_div(ceil_div(n, 4), 256);
+    k_emit_bwt<256><<<blocks, 256, 0, ctx->stream>>>(d_text, n, d_sa, d_bwt, &ctx->scalars->origin,
+                                                      (((uintptr_t)d_bwt) & 3) == 0 ? 1 : 0);
+    LAUNCHED();
+    return 0;
+}
+
+void finish_stats(dark_bwt_ctx* ctx, dark_bwt_stats* st, int e_first, int e_last) {
+    if (!st) return;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->events[e_first], ctx->events[e_last]);
+    st->device_ms = ms;
+    for (const auto& s : ctx->spans) {
+        if (s.e1 < 0) continue;
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ctx->events[s.e0], ctx->events[s.e1]);
+        switch (s.phase) {
+            case PH_INIT: st->init_ms += t; break;
+            case PH_SORT: st->sort_ms += t; break;
+            case PH_PASS: st->pass_ms += t; break;
+            case PH_KEYBUILD: st->keybuild_ms += t; break;
+            case PH_RERANK: st->rerank_ms += t; break;
+            case PH_EMIT: st->emit_ms += t; break;
+        }
+    }
+    st->kernel_launches = ctx->launches;
+}
+
+// The whole forward transform on device buffers.  d_sa_user nullable.
+int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64* origin_out, u32* d_sa_user,
+                   dark_bwt_stats* st) {
+    if (n64 < 2 || n64 > ctx->capacity || n64 > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;
+    const u32 n = (u32)n64;
+    CK(cudaSetDevice(ctx->device));
+    ctx->n_events = 0;
+    ctx->spans.clear();
+    ctx->next_counter = 0;
+    ctx->launches = 0;
+    if (st) {
+        const float h2d = st->h2d_ms;
+        memset(st, 0, sizeof(*st));
+        st->h2d_ms = h2d;
+        st->n = n;
+        st->active[0] = n;
+    }
+    u32* sa = d_sa_user ? d_sa_user : ctx->sa;
+
+    const int e_first = ctx->n_events++;
+    CK(cudaEventRecord(ctx->events[e_first], ctx->stream));
+
+    // ---- alphabet: sigma, dense codes, symbols per key
+    int sp = span_begin(ctx, PH_INIT);
+    CK(cudaMemsetAsync(ctx->counters, 0, sizeof(u32) * kMaxCounters, ctx->stream));
+    CK(cudaMemsetAsync(ctx->present, 0, sizeof(u32) * 256, ctx->stream));
+    CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
+    const int no_pack = (ctx->flags & DARK_BWT_F_NO_ALPHABET_PACKING) ? 1 : 0;
+    {
+        const u32 blocks = (u32)std::min<u64>(ceil_div(ceil_div(n, 16), 256), 148 * 8);
+        k_symbol_presence<256><<<std::max(blocks, 1u), 256, 0, ctx->stream>>>(d_text, n, ctx->present);
+        LAUNCHED();
+        k_build_lut<<<1, 256, 0, ctx->stream>>>(ctx->present, ctx->lut, &ctx->scalars->sigma, no_pack);
+        LAUNCHED();
+    }
+    CK(cudaMemcpyAsync(&ctx->mail->sigma, &ctx->scalars->sigma, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const u32 sigma = ctx->mail->sigma;
+    if (sigma < 1 || sigma > 256) return ctx->fail_internal("alphabet scan returned an impossible sigma");
+    const int s_bits = no_pack ? 8 : std::max(1, bit_length(sigma - 1));
+    const int K = 64 / s_bits;
+    const int passes0 = (s_bits * K + kRadixBits - 1) / kRadixBits;
+    if (st) {
+        st->sigma = sigma;
+        st->bits_per_symbol = s_bits;
+        st->symbols_per_key = K;
+    }
+
+    // ---- round 0: keys of K symbols, ids descending
+    {
+        const u32 blocks = (u32)ceil_div(n, kInitThreads * kInitItems);
+        k_init_keys<kInitThreads, kInitItems><<<blocks, kInitThreads, 0, ctx->stream>>>(
+            d_text, n, ctx->lut, s_bits, K, ctx->keys[0], ctx->ids[0], ctx->hist, passes0);
+        LAUNCHED();
+    }
+    span_end(ctx, sp);
+
+    int cur = 0;
+    sp = span_begin(ctx, PH_SORT);
+    if (int rc = run_sort(ctx, ctx->keys, ctx->ids, cur, n, 0, passes0, &cur, st, 0)) return rc;
+    span_end(ctx, sp);
+
+    const int kb = bit_length(n);  // rank2 = isa+1 in [0, n]
+    const int key_bits = kb + bit_length((u64)n - 1);
+    const int passes_r = (key_bits + kRadixBits - 1) / kRadixBits;
+
+    sp = span_begin(ctx, PH_RERANK);
+    if (int rc = launch_rerank<true>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, K, kb, sa, ctx->ids[cur ^ 1])) return rc;
+    span_end(ctx, sp);
+    cur ^= 1;  // the compacted active ids now live in ids[cur]
+    u32 m = 0;
+    if (int rc = fetch_count(ctx, &m)) return rc;
+
+    // ---- doubling rounds
+    u64 h = (u64)K;
+    int round = 1;
+    while (m > 0) {
+        if (round >= DARK_BWT_MAX_ROUNDS || h >= 2 * (u64)n + 2) return ctx->fail_internal("prefix doubling did not converge");
+        if (st) {
+            st->active[round] = m;
+            st->rounds = round;
+        }
+        sp = span_begin(ctx, PH_KEYBUILD);
+        CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
+        {
+            const u32 blocks = (u32)ceil_div(m, kBuildThreads * kBuildItems);
+            k_build_keys<kBuildThreads, kBuildItems><<<blocks, kBuildThreads, 0, ctx->stream>>>(
+                ctx->ids[cur], ctx->ranks, m, n, h, kb, ctx->isa, ctx->keys[cur], ctx->hist, passes_r);
+            LAUNCHED();
+        }
+        span_end(ctx, sp);
+
+        sp = span_begin(ctx, PH_SORT);
+        if (int rc = run_sort(ctx, ctx->keys, ctx->ids, cur, m, 0, passes_r, &cur, st, round)) return rc;
+        span_end(ctx, sp);
+
+        sp = span_begin(ctx, PH_RERANK);
+        if (int rc = launch_rerank<false>(ctx, ctx->keys[cur], ctx->ids[cur], m, n, K, kb, sa, ctx->ids[cur ^ 1])) return rc;
+        span_end(ctx, sp);
+        cur ^= 1;
+        if (int rc = fetch_count(ctx, &m)) return rc;
+        h *= 2;
+        ++round;
+    }
+
+    // ---- BWT bytes + origin
+    sp = span_begin(ctx, PH_EMIT);
+    if (int rc = emit(ctx, d_text, n, sa, d_bwt)) return rc;
+    span_end(ctx, sp);
+    const int e_last = ctx->n_events++;
+    CK(cudaEventRecord(ctx->events[e_last], ctx->stream));
+    CK(cudaMemcpyAsync(&ctx->mail->origin, &ctx->scalars->origin, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *origin_out = ctx->mail->origin;
+    finish_stats(ctx, st, e_first, e_last);
+    return DARK_BWT_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int dark_bwt_abi_version(void) { return DARK_BWT_ABI_VERSION; }
+
+const char* dark_bwt_strerror(int code) {
+    switch (code) {
+        case DARK_BWT_OK: return "ok";
+        case DARK_BWT_E_INVALID_N: return "invalid block length (need 2 <= n <= capacity and n <= 2^32-2)";
+        case DARK_BWT_E_INVALID_ARG: return "invalid argument";
+        case DARK_BWT_E_CUDA: return "CUDA failure";
+        case DARK_BWT_E_NOMEM: return "out of device or pinned host memory";
+        case DARK_BWT_E_INTERNAL: return "internal invariant violated";
+        default: return "unknown error";
+    }
+}
+
+const char* dark_bwt_last_error(const dark_bwt_ctx* ctx) { return ctx ? ctx->err : ""; }
+uint64_t dark_bwt_capacity(const dark_bwt_ctx* ctx) { return ctx ? ctx->capacity : 0; }
+void* dark_bwt_stream(const dark_bwt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int dark_bwt_create(uint64_t max_n, int device, dark_bwt_ctx** out) {
+    return dark_bwt_create_ex(max_n, device, DARK_BWT_F_DEFAULT, out);
+}
+
+int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx** out) {
+    if (!out) return DARK_BWT_E_INVALID_ARG;
+    *out = nullptr;
+    if (flags & ~(DARK_BWT_F_NO_ALPHABET_PACKING | DARK_BWT_F_DEVICE_ONLY)) return DARK_BWT_E_INVALID_ARG;
+    if (max_n < 2 || max_n > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return DARK_BWT_E_CUDA;  // no CPU fallback
+    if (device < 0 || device >= ndev) return DARK_BWT_E_INVALID_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return DARK_BWT_E_CUDA;
+
+    dark_bwt_ctx* ctx = new (std::nothrow) dark_bwt_ctx();
+    if (!ctx) return DARK_BWT_E_NOMEM;
+    ctx->device = device;
+    ctx->capacity = max_n;
+    ctx->flags = flags;
+
+    const size_t N = (size_t)max_n;
+    const size_t sort_tiles = ceil_div(N, kSortTile);
+    ctx->sort_status_bytes = sort_tiles * kRadix * sizeof(u64);
+    ctx->scan_tiles = ceil_div(N, kScanTile);
+    const bool staging = !(flags & DARK_BWT_F_DEVICE_ONLY);
+
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    const size_t o_keys0 = carve(N * 8), o_keys1 = carve(N * 8);
+    const size_t o_ids0 = carve(N * 4 + 16), o_ids1 = carve(N * 4 + 16);
+    const size_t o_ranks = carve(N * 4 + 16), o_isa = carve(N * 4 + 16), o_sa = carve(N * 4 + 16);
+    const size_t o_text = staging ? carve(N + 16) : 0, o_bwt = staging ? carve(N + 16) : 0;
+    const size_t o_hist = carve(sizeof(u32) * kMaxPasses * kRadix);
+    const size_t o_present = carve(sizeof(u32) * 256);
+    const size_t o_lut = carve(256);
+    const size_t o_scalars = carve(sizeof(DeviceScalars));
+    const size_t o_status = carve(ctx->sort_status_bytes);
+    const size_t o_counters = carve(sizeof(u32) * kMaxCounters);
+    const size_t o_sflag = carve(sizeof(u32) * ctx->scan_tiles);
+    const size_t o_sagg = carve(sizeof(uint4) * ctx->scan_tiles);
+    const size_t o_sincl = carve(sizeof(uint4) * ctx->scan_tiles);
+    ctx->arena_bytes = off;
+
+    auto bail = [&](int code) {
+        dark_bwt_destroy(ctx);
+        return code;
+    };
+    if (cudaMalloc(&ctx->arena, ctx->arena_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->arena = nullptr;
+        return bail(DARK_BWT_E_NOMEM);
+    }
+    char* base = (char*)ctx->arena;
+    ctx->keys[0] = (u64*)(base + o_keys0);
+    ctx->keys[1] = (u64*)(base + o_keys1);
+    ctx->ids[0] = (u32*)(base + o_ids0);
+    ctx->ids[1] = (u32*)(base + o_ids1);
+    ctx->ranks = (u32*)(base + o_ranks);
+    ctx->isa = (u32*)(base + o_isa);
+    ctx->sa = (u32*)(base + o_sa);
+    ctx->d_text = staging ? (u8*)(base + o_text) : nullptr;
+    ctx->d_bwt = staging ? (u8*)(base + o_bwt) : nullptr;
+    ctx->hist = (u32*)(base + o_hist);
+    ctx->present = (u32*)(base + o_present);
+    ctx->lut = (u8*)(base + o_lut);
+    ctx->scalars = (DeviceScalars*)(base + o_scalars);
+    ctx->sort_status = base + o_status;
+    ctx->counters = (u32*)(base + o_counters);
+    ctx->scan_flag = (u32*)(base + o_sflag);
+    ctx->scan_agg = (uint4*)(base + o_sagg);
+    ctx->scan_incl = (uint4*)(base + o_sincl);
+
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DARK_BWT_E_CUDA);
+    if (cudaHostAlloc((void**)&ctx->mail, sizeof(Mailbox), cudaHostAllocDefault) != cudaSuccess) return bail(DARK_BWT_E_NOMEM);
+    memset(ctx->mail, 0, sizeof(Mailbox));
+    for (int i = 0; i < kMaxEvents; ++i) {
+        ctx->events[i] = nullptr;
+        if (cudaEventCreate(&ctx->events[i]) != cudaSuccess) return bail(DARK_BWT_E_CUDA);
+    }
+    typedef OnesweepSmem<kSortThreads, kSortItems> Smem;
+    if (cudaFuncSetAttribute(k_onesweep_pass<kSortThreads, kSortItems, u32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(Smem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_onesweep_pass<kSortThreads, kSortItems, u64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(Smem)) != cudaSuccess)
+        return bail(DARK_BWT_E_CUDA);
+    if (cudaMemsetAsync(ctx->scalars, 0, sizeof(DeviceScalars), ctx->stream) != cudaSuccess) return bail(DARK_BWT_E_CUDA);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return bail(DARK_BWT_E_CUDA);
+    *out = ctx;
+    return DARK_BWT_OK;
+}
+
+void dark_bwt_destroy(dark_bwt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < kMaxEvents; ++i)
+        if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->mail) cudaFreeHost(ctx->mail);
+    if (ctx->arena) cudaFree(ctx->arena);
+    free(ctx->reuse_words);
+    delete ctx;
+}
+
+int dark_bwt_forward_device(dark_bwt_ctx* ctx, const uint8_t* d_text, uint64_t n, uint8_t* d_bwt_out, uint64_t* origin_out,
+                            uint32_t* d_sa_out, dark_bwt_stats* stats) {
+    if (!ctx || !d_text || !d_bwt_out || !origin_out) return DARK_BWT_E_INVALID_ARG;
+    ctx->err[0] = 0;
+    if (stats) stats->h2d_ms = 0.f;
+    return forward_device(ctx, d_text, n, d_bwt_out, origin_out, d_sa_out, stats);
+}
+
+int dark_bwt_forward(dark_bwt_ctx* ctx, const uint8_t* text, uint64_t n, uint8_t* bwt_out, uint64_t* origin_out,
+                     uint32_t* sa_out, dark_bwt_stats* stats) {
+    if (!ctx || !text || !bwt_out || !origin_out) return DARK_BWT_E_INVALID_ARG;
+    ctx->err[0] = 0;
+    if (ctx->flags & DARK_BWT_F_DEVICE_ONLY) return DARK_BWT_E_INVALID_ARG;
+    if (n < 2 || n > ctx->capacity || n > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;
+    CK(cudaSetDevice(ctx->device));
+    cudaEvent_t a = ctx->events[kMaxEvents - 1], b = ctx->events[kMaxEvents - 2];
+    CK(cudaEventRecord(a, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_text, text, n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float h2d = 0.f;
+    cudaEventElapsedTime(&h2d, a, b);
+    if (stats) stats->h2d_ms = h2d;
+    int rc = forward_device(ctx, ctx->d_text, n, ctx->d_bwt, origin_out, nullptr, stats);
+    if (rc) return rc;
+    CK(cudaEventRecord(a, ctx->stream));
+    CK(cudaMemcpyAsync(bwt_out, ctx->d_bwt, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sa_out) CK(cudaMemcpyAsync(sa_out, ctx->sa, n * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (stats) cudaEventElapsedTime(&stats->d2h_ms, a, b);
+    return DARK_BWT_OK;
+}
+
+int dark_bwt_reuse(dark_bwt_ctx* ctx, uint32_t** words_out, uint64_t* count_out) {
+    if (!ctx || !words_out || !count_out) return DARK_BWT_E_INVALID_ARG;
+    if (!ctx->reuse_words) {
+        // same size as the reference arena: n + 0x100 + max(n/4, min(2^15+2^7, n/2))  (saca.rs:353-357)
+        const u64 n = ctx->capacity;
+        const u64 extra = 0x100 + std::max<u64>(n / 4, std::min<u64>((1ull << 15) + (1ull << 7), n / 2));
+        ctx->reuse_words = (u32*)calloc((size_t)(n + extra), sizeof(u32));
+        if (!ctx->reuse_words) return DARK_BWT_E_NOMEM;
+        ctx->reuse_count = n + extra;
+    }
+    *words_out = ctx->reuse_words;
+    *count_out = ctx->reuse_count;
+    return DARK_BWT_OK;
+}
+
+int dark_bwt_sort_pairs_device(dark_bwt_ctx* ctx, uint64_t* d_keys, uint32_t* d_vals, uint64_t* d_keys_alt,
+                               uint32_t* d_vals_alt, uint64_t count, int begin_bit, int end_bit, int* in_alt_out,
+                               float* ms_out) {
+    if (!ctx || !d_keys || !d_vals || !d_keys_alt || !d_vals_alt || !in_alt_out) return DARK_BWT_E_INVALID_ARG;
+    if (begin_bit < 0 || end_bit > 64 || begin_bit >= end_bit) return DARK_BWT_E_INVALID_ARG;
+    if (count == 0 || count > ctx->capacity) return DARK_BWT_E_INVALID_N;
+    ctx->err[0] = 0;
+    CK(cudaSetDevice(ctx->device));
+    const u32 m = (u32)count;
+    const int num_passes = (end_bit - begin_bit + kRadixBits - 1) / kRadixBits;
+    ctx->next_counter = 0;
+    ctx->n_events = 0;
+    ctx->spans.clear();
+    CK(cudaMemsetAsync(ctx->counters, 0, sizeof(u32) * kMaxCounters, ctx->stream));
+    CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
+    cudaEvent_t a = ctx->events[kMaxEvents - 1], b = ctx->events[kMaxEvents - 2];
+    CK(cudaEventRecord(a, ctx->stream));
+    const u32 blocks = (u32)std::min<u64>(ceil_div(m, 256 * 8), 148 * 8);
+    k_digit_hist<256><<<blocks, 256, 0, ctx->stream>>>(d_keys, m, begin_bit, num_passes, ctx->hist);
+    LAUNCHED();
+    u64* keys[2] = {d_keys, d_keys_alt};
+    u32* vals[2] = {d_vals, d_vals_alt};
+    int cur = 0;
+    // note: a partial top digit needs no masking as long as the bits above end_bit are equal in
+    // all keys or meant to take part; callers pass end_bit = 64 or keys with zero upper bits.
+    if (int rc = run_sort(ctx, keys, vals, 0, m, begin_bit, num_passes, &cur, nullptr, 0)) return rc;
+    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ms_out) cudaEventElapsedTime(ms_out, a, b);
+    *in_alt_out = cur;
+    return DARK_BWT_OK;
+}
+
+int dark_bwt_verify_sa_device(dark_bwt_ctx* ctx, const uint8_t* d_text, uint64_t n64, const uint32_t* d_sa,
+                              uint64_t* bad_out) {
+    if (!ctx || !d_text || !d_sa || !bad_out) return DARK_BWT_E_INVALID_ARG;
+    if (n64 < 1 || n64 > ctx->capacity) return DARK_BWT_E_INVALID_N;
+    ctx->err[0] = 0;
+    CK(cudaSetDevice(ctx->device));
+    const u32 n = (u32)n64;
+    CK(cudaMemsetAsync(&ctx->scalars->bad, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->isa, 0xFF, sizeof(u32) * (size_t)n, ctx->stream));
+    const u32 blocks = (u32)ceil_div(n, 256);
+    k_verify_scatter<256><<<blocks, 256, 0, ctx->stream>>>(d_sa, n, ctx->isa, &ctx->scalars->bad);
+    LAUNCHED();
+    k_verify_order<256><<<blocks, 256, 0, ctx->stream>>>(d_text, d_sa, n, ctx->isa, &ctx->scalars->bad);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(&ctx->mail->bad, &ctx->scalars->bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *bad_out = ctx->mail->bad;
+    return DARK_BWT_OK;
+}
+
+int dark_bwt_emit_device(dark_bwt_ctx* ctx, const uint8_t* d_text, uint64_t n, const uint32_t* d_sa, uint8_t* d_bwt_out,
+                         uint64_t* origin_out) {
+    if (!ctx || !d_text || !d_sa || !d_bwt_out || !origin_out) return DARK_BWT_E_INVALID_ARG;
+    if (n < 1 || n > ctx->capacity || n > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;
+    ctx->err[0] = 0;
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = emit(ctx, d_text, (u32)n, d_sa, d_bwt_out)) return rc;
+    CK(cudaMemcpyAsync(&ctx->mail->origin, &ctx->scalars->origin, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *origin_out = ctx->mail->origin;
+    return DARK_BWT_OK;
+}
+
+}  // extern "C"

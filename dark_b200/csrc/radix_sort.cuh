@@ -1,0 +1,235 @@
+// radix_sort.cuh — LSD radix sort of (u64 key, u32 value) pairs in "onesweep" form:
+// one upfront multi-digit histogram, then ONE kernel per 8-bit digit that reads each pair
+// once and writes it once, chaining the per-tile digit counts with a decoupled look-back.
+//
+// This is the sort under the prefix-doubling suffix sorter that replaces the induced-sorting
+// sweeps of the reference (put_substr/induce_low/induce_sup, /root/reference/src/saca.rs:60-163):
+// keys are packed (rank[i], rank[i+h]) pairs, values are suffix indices.
+//
+// Roofline: HBM-bound.  Algorithmic bytes per pass launch = 24 B/pair (12 read + 12 written);
+// the histogram adds one 8 B/pair read per sort (fused into the key builders on the hot path).
+#pragma once
+
+#include "common.cuh"
+
+namespace dark {
+
+__device__ __forceinline__ u32 digit_of(u64 key, int shift) { return (u32)(key >> shift) & (kRadix - 1); }
+
+// ---- shared-memory digit histogram for all passes of a sort -----------------------------------
+// s_hist: [kMaxPasses][kRadix] u32, zeroed by the caller.
+__device__ __forceinline__ void hist_add_key(u32* s_hist, u64 key, int begin_bit, int num_passes) {
+#pragma unroll
+    for (int p = 0; p < kMaxPasses; ++p) {
+        if (p < num_passes) atomicAdd(&s_hist[p * kRadix + digit_of(key, begin_bit + p * kRadixBits)], 1u);
+    }
+}
+__device__ __forceinline__ void hist_clear(u32* s_hist, int tid, int nthreads) {
+    for (int i = tid; i < kMaxPasses * kRadix; i += nthreads) s_hist[i] = 0;
+}
+__device__ __forceinline__ void hist_flush(u32* s_hist, u32* g_hist, int num_passes, int tid, int nthreads) {
+    for (int i = tid; i < num_passes * kRadix; i += nthreads) {
+        u32 c = s_hist[i];
+        if (c) atomicAdd(&g_hist[i], c);
+    }
+}
+
+// Stand-alone histogram (used when the keys were not produced by one of the fused builders).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_digit_hist(const u64* __restrict__ keys, u32 m, int begin_bit,
+                                                        int num_passes, u32* __restrict__ g_hist) {
+    __shared__ u32 s_hist[kMaxPasses * kRadix];
+    hist_clear(s_hist, threadIdx.x, THREADS);
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * THREADS;
+    for (u64 i = (u64)blockIdx.x * THREADS + threadIdx.x; i < m; i += stride)
+        hist_add_key(s_hist, ld_stream(keys + i), begin_bit, num_passes);
+    __syncthreads();
+    hist_flush(s_hist, g_hist, num_passes, threadIdx.x, THREADS);
+}
+
+// Counts -> exclusive digit bases, in place; one CTA of kRadix threads per pass.
+// trivial[p] = 1 when a single digit holds all m keys (the pass would be the identity).
+__global__ void __launch_bounds__(kRadix) k_scan_hist(u32* __restrict__ g_hist, u32 m, u32* __restrict__ trivial) {
+    __shared__ u32 s_warp[kRadix / 32];
+    __shared__ u32 s_triv;
+    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    u32* row = g_hist + blockIdx.x * kRadix;
+    if (d == 0) s_triv = 0;
+    __syncthreads();
+    const u32 c = row[d];
+    if (c == m) s_triv = 1;
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    u32 base = 0;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    row[d] = base + incl - c;
+    if (d == 0) trivial[blockIdx.x] = s_triv;
+}
+
+// ---- the onesweep pass ------------------------------------------------------------------------
+// Tile status word: [flag | value]; flag 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix.
+template <typename StatusT>
+struct StatusTraits;
+template <>
+struct StatusTraits<u32> {
+    static constexpr int kShift = 30;
+    static constexpr u32 kMask = (1u << 30) - 1;
+};
+template <>
+struct StatusTraits<u64> {
+    static constexpr int kShift = 62;
+    static constexpr u64 kMask = (1ull << 62) - 1;
+};
+
+template <int THREADS, int ITEMS>
+struct OnesweepSmem {
+    static constexpr int kTile = THREADS * ITEMS;
+    static constexpr int kWarps = THREADS / 32;
+    u64 keys[kTile];             // tile re-ordered by digit (so the global scatter is run-coalesced)
+    u32 vals[kTile];
+    u32 warp_hist[kWarps][kRadix];  // per-warp digit counters -> exclusive warp offsets
+    u32 digit_start[kRadix];        // exclusive scan of the tile's digit counts
+    u32 global_off[kRadix];         // output index of local position 0 of each digit (mod 2^32)
+    u32 warp_sum[kRadix / 32];
+    u32 tile;
+};
+
+template <int THREADS, int ITEMS, typename StatusT>
+__global__ void __launch_bounds__(THREADS)
+k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
+                u32* __restrict__ vals_out, u32 m, int shift, const u32* __restrict__ digit_base,
+                StatusT* __restrict__ status, u32* __restrict__ tile_counter) {
+    static_assert(THREADS >= kRadix && THREADS % 32 == 0, "one thread per digit is assumed");
+    typedef OnesweepSmem<THREADS, ITEMS> Smem;
+    typedef StatusTraits<StatusT> ST;
+    constexpr int TILE = Smem::kTile;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // Tiles are claimed in launch order so that every predecessor of a tile is already running:
+    // the look-back below never waits on a CTA that has not been scheduled.
+    if (tid == 0) s.tile = atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < Smem::kWarps * kRadix; i += THREADS) (&s.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const u32 tile = s.tile;
+    const u64 tile_base = (u64)tile * TILE;
+    const u32 nvalid = (u32)min((u64)TILE, (u64)m - tile_base);
+
+    // warp-striped arrangement: element (warp, k, lane) has tile-local index warp*32*ITEMS + k*32 + lane,
+    // so every load instruction of a warp covers 32 consecutive pairs and rank order == index order.
+    const u32 local0 = warp * (32 * ITEMS) + lane;
+    u64 key[ITEMS];
+    u32 val[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u32 li = local0 + k * 32;
+        key[k] = (li < nvalid) ? ld_stream(keys_in + tile_base + li) : ~0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u32 li = local0 + k * 32;
+        val[k] = (li < nvalid) ? ld_stream(vals_in + tile_base + li) : 0u;
+    }
+
+    // ---- rank inside the warp: match_any groups equal digits, the lowest lane bumps the counter
+    u32 rank[ITEMS];
+    u32* whist = s.warp_hist[warp];
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const bool valid = (local0 + k * 32) < nvalid;
+        const u32 d = valid ? digit_of(key[k], shift) : (u32)kRadix;  // invalid lanes group apart
+        const u32 peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        u32 prev = 0;
+        if (lane == leader && valid) {
+            prev = whist[d];
+            whist[d] = prev + __popc(peers);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        rank[k] = prev + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per-digit: exclusive offsets across warps, tile total, publish, look back
+    u32 count = 0;
+    if (tid < kRadix) {
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < Smem::kWarps; ++w) {
+            const u32 c = s.warp_hist[w][tid];
+            s.warp_hist[w][tid] = run;
+            run += c;
+        }
+        count = run;
+        StatusT* slot = status + (size_t)tile * kRadix + tid;
+        st_relaxed(slot, ((StatusT)(tile == 0 ? 2 : 1) << ST::kShift) | (StatusT)count);
+    }
+    // exclusive scan of the 256 digit counts (threads >= 256 contribute 0 and are ignored)
+    u32 incl = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (tid < kRadix && lane == 31) s.warp_sum[warp] = incl;
+    __syncthreads();
+    if (tid < kRadix) {
+        u32 wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += s.warp_sum[w];
+        const u32 dstart = wbase + incl - count;
+        s.digit_start[tid] = dstart;
+
+        StatusT excl = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            for (;;) {
+                const StatusT v = ld_relaxed(status + (size_t)t * kRadix + tid);
+                const u32 flag = (u32)(v >> ST::kShift);
+                if (flag == 0) continue;  // predecessor has not published yet
+                excl += v & ST::kMask;
+                if (flag == 2) break;
+                --t;
+            }
+            st_relaxed(status + (size_t)tile * kRadix + tid, ((StatusT)2 << ST::kShift) | (excl + count));
+        }
+        s.global_off[tid] = digit_base[tid] + (u32)excl - dstart;
+    }
+    __syncthreads();
+
+    // ---- re-order the tile by digit in shared memory
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if ((local0 + k * 32) < nvalid) {
+            const u32 d = digit_of(key[k], shift);
+            const u32 pos = s.digit_start[d] + whist[d] + rank[k];
+            s.keys[pos] = key[k];
+            s.vals[pos] = val[k];
+        }
+    }
+    __syncthreads();
+
+    // ---- scatter: consecutive threads write consecutive addresses inside each digit run
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u32 p = k * THREADS + tid;
+        if (p < nvalid) {
+            const u64 kk = s.keys[p];
+            const u32 idx = s.global_off[digit_of(kk, shift)] + p;
+            keys_out[idx] = kk;
+            vals_out[idx] = s.vals[p];
+        }
+    }
+}
+
+}  // namespace dark

@@ -1,0 +1,444 @@
+// suffix_kernels.cuh — the prefix-doubling suffix sorter around the radix sort, and BWT emission.
+//
+// Replaces (results, not internals) the reference's SA-IS `saca()` (/root/reference/src/saca.rs:270-340)
+// and `compress::bwt::TransformIterator` (call sites src/block/dc.rs:45-50, src/block/raw.rs:39-44).
+//
+// Order convention: plain lexicographic order of suffixes, a proper prefix
+// sorts first.  There is no in-band sentinel: "beyond the end" is rank 0, real ranks are stored
+// 0-based in isa[] and read as isa[i]+1.
+#pragma once
+
+#include "common.cuh"
+#include "radix_sort.cuh"
+
+namespace dark {
+
+// ---- alphabet ---------------------------------------------------------------------------------
+// Which byte values occur?  (HBM: N bytes read.)  Plain racing stores of the constant 1 are fine.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_symbol_presence(const u8* __restrict__ text, u64 n, u32* __restrict__ present) {
+    __shared__ u32 s_present[256];
+    for (int i = threadIdx.x; i < 256; i += THREADS) s_present[i] = 0;
+    __syncthreads();
+    // 16-byte aligned body, scalar head and tail
+    const u64 addr = (u64)text;
+    u64 head = (16 - (addr & 15)) & 15;
+    if (head > n) head = n;
+    const u64 nvec = (n - head) / 16;
+    const uint4* body = reinterpret_cast<const uint4*>(text + head);
+    const u64 gtid = (u64)blockIdx.x * THREADS + threadIdx.x, gstride = (u64)gridDim.x * THREADS;
+    for (u64 v = gtid; v < nvec; v += gstride) {
+        const uint4 q = __ldg(body + v);
+        const u32 w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            s_present[w[a] & 255] = 1;
+            s_present[(w[a] >> 8) & 255] = 1;
+            s_present[(w[a] >> 16) & 255] = 1;
+            s_present[w[a] >> 24] = 1;
+        }
+    }
+    if (gtid < head) s_present[text[gtid]] = 1;
+    const u64 tail0 = head + nvec * 16;
+    if (tail0 + gtid < n && gtid < 16) s_present[text[tail0 + gtid]] = 1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += THREADS)
+        if (s_present[i]) present[i] = 1;
+}
+
+// present[256] -> dense codes (rank among the present symbols) and sigma.  One CTA of 256 threads.
+__global__ void __launch_bounds__(256) k_build_lut(const u32* __restrict__ present, u8* __restrict__ lut, u32* __restrict__ sigma_out,
+                                                   int identity) {
+    __shared__ u32 s_warp[8];
+    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    const u32 c = present[d] ? 1u : 0u;
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    u32 base = 0;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    lut[d] = identity ? (u8)d : (u8)(base + incl - c);
+    if (d == 255) *sigma_out = base + incl;
+}
+
+// ---- round 0: initial keys ----------------------------------------------------------------------
+// Element j of the sort input is suffix id = n-1-j (descending), key = the first K symbols of the
+// suffix as dense s-bit codes, most significant first, zero-padded past the end of the text.
+// The descending order makes the STABLE LSD sort break ties between a short (padded) suffix and
+// longer ones with the same key the right way: the shorter suffix comes first (App. A.3).
+// Fused: digit histogram of all passes.  HBM: N read, 12 N written.
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+k_init_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ lut, int s_bits, int K, u64* __restrict__ keys_out,
+            u32* __restrict__ ids_out, u32* __restrict__ g_hist, int num_passes) {
+    constexpr int TILE = THREADS * ITEMS;
+    __shared__ u8 s_code[TILE + 64];
+    __shared__ u8 s_lut[256];
+    __shared__ u32 s_hist[kMaxPasses * kRadix];
+    const int tid = threadIdx.x;
+    hist_clear(s_hist, tid, THREADS);
+    for (int i = tid; i < 256; i += THREADS) s_lut[i] = lut[i];
+    __syncthreads();
+
+    const u64 jb = (u64)blockIdx.x * TILE;
+    const u32 cnt = (u32)min((u64)TILE, (u64)n - jb);
+    const u64 i_lo = (u64)n - jb - cnt;  // lowest text position of this tile
+    const u32 span = cnt + K - 1;
+    for (u32 x = tid; x < span; x += THREADS) {
+        const u64 pos = i_lo + x;
+        s_code[x] = pos < n ? s_lut[text[pos]] : (u8)0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < ITEMS; ++k) {
+        const u32 jl = k * THREADS + tid;
+        if (jl < cnt) {
+            const u32 x = cnt - 1 - jl;  // position i = i_lo + x
+            u64 key = 0;
+            for (int c = 0; c < K; ++c) key = (key << s_bits) | s_code[x + c];
+            keys_out[jb + jl] = key;
+            ids_out[jb + jl] = (u32)(i_lo + x);
+            hist_add_key(s_hist, key, 0, num_passes);
+        }
+    }
+    __syncthreads();
+    hist_flush(s_hist, g_hist, num_passes, tid, THREADS);
+}
+
+// ---- round r >= 1: keys (rank[i], rank[i+h]) ------------------------------------------------------
+// Active element p: suffix ids[p] in a group of rank ranks[p].  key = rank << kb | (isa[i+h]+1 or 0).
+// Fused: digit histogram.  HBM: 8 B read + one 4-byte gather (a 32 B sector) + 8 B written per element.
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+k_build_keys(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m, u32 n, u64 h, int kb,
+             const u32* __restrict__ isa, u64* __restrict__ keys_out, u32* __restrict__ g_hist, int num_passes) {
+    __shared__ u32 s_hist[kMaxPasses * kRadix];
+    const int tid = threadIdx.x;
+    hist_clear(s_hist, tid, THREADS);
+    __syncthreads();
+    const u64 base = (u64)blockIdx.x * (THREADS * ITEMS);
+    u32 id[ITEMS], r2[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u64 p = base + k * THREADS + tid;
+        id[k] = p < m ? ld_stream(ids + p) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u64 p = base + k * THREADS + tid;
+        const u64 pos2 = (u64)id[k] + h;
+        r2[k] = (p < m && pos2 < n) ? __ldg(isa + pos2) + 1u : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u64 p = base + k * THREADS + tid;
+        if (p < m) {
+            const u64 key = ((u64)ld_stream(ranks + p) << kb) | r2[k];
+            keys_out[p] = key;
+            hist_add_key(s_hist, key, 0, num_passes);
+        }
+    }
+    __syncthreads();
+    hist_flush(s_hist, g_hist, num_passes, tid, THREADS);
+}
+
+// ---- re-rank + compaction: one decoupled look-back scan ------------------------------------------
+// Input: the active list sorted by key.  A "new head" starts a run of equal keys (= a group of
+// suffixes still tied after 2h symbols); an "old head" starts a run of equal key>>kb (the group the
+// run was split from).  With gs/hs the indices of the latest old/new head at or before p:
+//     new rank(p) = old rank + (hs - gs)        (= global SA slot of the new group's first member)
+// A new group of size 1 is settled: SA[rank] = id, and it is dropped from the active list.
+// The scan carries (latest old head + 1, latest new head + 1, survivors so far).
+struct ScanTriple {
+    u32 gs1, hs1, cnt;
+};
+__device__ __forceinline__ ScanTriple scan_combine(ScanTriple a, ScanTriple b) {  // a earlier, b later
+    ScanTriple r;
+    r.gs1 = max(a.gs1, b.gs1);
+    r.hs1 = max(a.hs1, b.hs1);
+    r.cnt = a.cnt + b.cnt;
+    return r;
+}
+__device__ __forceinline__ ScanTriple shfl_up_triple(ScanTriple v, int o) {
+    ScanTriple r;
+    r.gs1 = __shfl_up_sync(0xffffffffu, v.gs1, o);
+    r.hs1 = __shfl_up_sync(0xffffffffu, v.hs1, o);
+    r.cnt = __shfl_up_sync(0xffffffffu, v.cnt, o);
+    return r;
+}
+__device__ __forceinline__ ScanTriple shfl_xor_triple(ScanTriple v, int o) {
+    ScanTriple r;
+    r.gs1 = __shfl_xor_sync(0xffffffffu, v.gs1, o);
+    r.hs1 = __shfl_xor_sync(0xffffffffu, v.hs1, o);
+    r.cnt = __shfl_xor_sync(0xffffffffu, v.cnt, o);
+    return r;
+}
+__device__ __forceinline__ void st_payload(uint4* p, ScanTriple v) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.gs1), "r"(v.hs1), "r"(v.cnt), "r"(0u)
+                 : "memory");
+}
+__device__ __forceinline__ ScanTriple ld_payload(const uint4* p) {
+    ScanTriple v;
+    u32 pad;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.gs1), "=r"(v.hs1), "=r"(v.cnt), "=r"(pad) : "l"(p) : "memory");
+    return v;
+}
+
+// Scan tile descriptors: flag[t] (0 = empty, 1 = aggregate ready, 2 = inclusive ready) with the
+// payloads in separate write-once arrays; payload store -> fence -> flag store on the producer,
+// flag load -> fence -> payload load on the consumer.
+struct ScanTileState {
+    u32* flag;
+    uint4* agg;
+    uint4* incl;
+};
+
+template <int THREADS, int ITEMS, bool ROUND0>
+__global__ void __launch_bounds__(THREADS)
+k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n, int K, int kb, u32* __restrict__ isa,
+         u32* __restrict__ sa, u32* __restrict__ out_ids, u32* __restrict__ out_ranks, ScanTileState ts,
+         u32* __restrict__ tile_counter, u32* __restrict__ out_count) {
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int WARPS = THREADS / 32;
+    __shared__ ScanTriple s_warp[WARPS];
+    __shared__ ScanTriple s_excl;
+    __shared__ u32 s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 p0 = (u64)tile * TILE + (u64)tid * ITEMS;  // blocked arrangement
+
+    // keys[p0-1 .. p0+ITEMS], ids[p0 .. p0+ITEMS) (+ neighbours in round 0)
+    u64 key[ITEMS + 2];
+    u32 id[ITEMS + 2];
+    if (p0 + ITEMS <= m) {
+        const ulonglong2* kv = reinterpret_cast<const ulonglong2*>(keys + p0);
+#pragma unroll
+        for (int k = 0; k < ITEMS / 2; ++k) {
+            const ulonglong2 q = kv[k];
+            key[1 + 2 * k] = q.x;
+            key[2 + 2 * k] = q.y;
+        }
+        const uint4* iv = reinterpret_cast<const uint4*>(ids + p0);
+#pragma unroll
+        for (int k = 0; k < ITEMS / 4; ++k) {
+            const uint4 q = iv[k];
+            id[1 + 4 * k] = q.x;
+            id[2 + 4 * k] = q.y;
+            id[3 + 4 * k] = q.z;
+            id[4 + 4 * k] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            key[1 + k] = (p0 + k < m) ? keys[p0 + k] : 0;
+            id[1 + k] = (p0 + k < m) ? ids[p0 + k] : 0;
+        }
+    }
+    key[0] = (p0 > 0 && p0 - 1 < m) ? keys[p0 - 1] : 0;
+    key[ITEMS + 1] = (p0 + ITEMS < m) ? keys[p0 + ITEMS] : 0;
+    if (ROUND0) {
+        id[0] = (p0 > 0 && p0 - 1 < m) ? ids[p0 - 1] : 0;
+        id[ITEMS + 1] = (p0 + ITEMS < m) ? ids[p0 + ITEMS] : 0;
+    }
+
+    // head flags for p0 .. p0+ITEMS (the last one is the look-ahead of item ITEMS-1)
+    const u64 short_from = (u64)n >= (u64)K ? (u64)n - K + 1 : 0;  // suffix i is "short" (key padded) iff i >= short_from
+    u32 newh = 0, oldh = 0;  // bit k: element p0+k starts a new / an old group
+#pragma unroll
+    for (int k = 0; k <= ITEMS; ++k) {
+        const u64 p = p0 + k;
+        bool nh, oh;
+        if (p >= m) {
+            nh = true;
+            oh = true;
+        } else if (p == 0) {
+            nh = true;
+            oh = true;
+        } else {
+            nh = key[k + 1] != key[k];
+            if (ROUND0) {
+                nh = nh || id[k + 1] >= short_from || id[k] >= short_from;
+                oh = false;
+            } else {
+                oh = (key[k + 1] >> kb) != (key[k] >> kb);
+            }
+        }
+        newh |= (nh ? 1u : 0u) << k;
+        oldh |= (oh ? 1u : 0u) << k;
+    }
+
+    // thread aggregate
+    ScanTriple agg = {0u, 0u, 0u};
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u64 p = p0 + k;
+        if (p < m) {
+            if ((oldh >> k) & 1) agg.gs1 = (u32)p + 1;
+            if ((newh >> k) & 1) agg.hs1 = (u32)p + 1;
+            const bool single = ((newh >> k) & 1) && ((newh >> (k + 1)) & 1);
+            agg.cnt += single ? 0u : 1u;
+        }
+    }
+    // block-wide exclusive scan of the thread aggregates
+    ScanTriple incl = agg;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        ScanTriple t = shfl_up_triple(incl, o);
+        if (lane >= o) incl = scan_combine(t, incl);
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    ScanTriple wprefix = {0u, 0u, 0u};
+    for (int w = 0; w < warp; ++w) wprefix = scan_combine(wprefix, s_warp[w]);
+    ScanTriple texcl = shfl_up_triple(incl, 1);
+    if (lane == 0) texcl = ScanTriple{0u, 0u, 0u};
+    texcl = scan_combine(wprefix, texcl);  // exclusive prefix of this thread inside the tile
+
+    // tile aggregate -> publish, look back (warp 0)
+    if (warp == 0) {
+        ScanTriple tile_agg = {0u, 0u, 0u};
+        for (int w = 0; w < WARPS; ++w) tile_agg = scan_combine(tile_agg, s_warp[w]);
+        ScanTriple excl = {0u, 0u, 0u};
+        if (tile == 0) {
+            if (lane == 0) {
+                st_payload(ts.incl + 0, tile_agg);
+                __threadfence();
+                st_relaxed(ts.flag + 0, 2u);
+            }
+        } else {
+            if (lane == 0) {
+                st_payload(ts.agg + tile, tile_agg);
+                __threadfence();
+                st_relaxed(ts.flag + tile, 1u);
+            }
+            int base = (int)tile - 1;
+            for (;;) {
+                const int t = base - lane;
+                u32 f = 2;
+                if (t >= 0) {
+                    do {
+                        f = ld_relaxed(ts.flag + t);
+                    } while (f == 0);
+                }
+                __threadfence();
+                ScanTriple v = {0u, 0u, 0u};
+                if (t >= 0) v = ld_payload((f == 2 ? ts.incl : ts.agg) + t);
+                const u32 im = __ballot_sync(0xffffffffu, f == 2);
+                const int first = im ? (__ffs(im) - 1) : 32;  // nearest tile with an inclusive prefix
+                if (lane > first) v = ScanTriple{0u, 0u, 0u};
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v = scan_combine(v, shfl_xor_triple(v, o));  // ops commute
+                excl = scan_combine(v, excl);
+                if (im) break;
+                base -= 32;
+            }
+            if (lane == 0) {
+                st_payload(ts.incl + tile, scan_combine(excl, tile_agg));
+                __threadfence();
+                st_relaxed(ts.flag + tile, 2u);
+            }
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if ((u64)(tile + 1) * TILE >= m) *out_count = excl.cnt + tile_agg.cnt;  // last tile: survivors in total
+        }
+    }
+    __syncthreads();
+    ScanTriple run = scan_combine(s_excl, texcl);
+
+    // apply
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u64 p = p0 + k;
+        if (p < m) {
+            if ((oldh >> k) & 1) run.gs1 = (u32)p + 1;
+            if ((newh >> k) & 1) run.hs1 = (u32)p + 1;
+            const u32 r_old = ROUND0 ? 0u : (u32)(key[k + 1] >> kb);
+            const u32 r_new = r_old + (run.hs1 - run.gs1);
+            const u32 sid = id[k + 1];
+            const bool single = ((newh >> k) & 1) && ((newh >> (k + 1)) & 1);
+            if (ROUND0 || r_new != r_old) isa[sid] = r_new;
+            if (single) {
+                sa[r_new] = sid;
+            } else {
+                out_ids[run.cnt] = sid;
+                out_ranks[run.cnt] = r_new;
+                run.cnt += 1;
+            }
+        }
+    }
+}
+
+// ---- BWT emission ---------------------------------------------------------------------------------
+// bwt[j] = T[SA[j]-1]; the single j with SA[j]==0 takes T[n-1] and is the origin
+// (TransformIterator; known answers /root/reference/src/saca.rs:411-412).
+// HBM: 4 N read (SA, 128-bit loads), N random byte gathers (one 32 B sector each), N written.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_emit_bwt(const u8* __restrict__ text, u32 n, const u32* __restrict__ sa, u8* __restrict__ bwt, u64* __restrict__ origin,
+           int bwt_aligned4) {
+    const u64 j0 = ((u64)blockIdx.x * THREADS + threadIdx.x) * 4;
+    if (j0 >= n) return;
+    u32 s[4];
+    if (j0 + 4 <= n) {
+        const uint4 q = *reinterpret_cast<const uint4*>(sa + j0);
+        s[0] = q.x; s[1] = q.y; s[2] = q.z; s[3] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s[k] = (j0 + k < n) ? sa[j0 + k] : 1u;
+    }
+    u32 b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const u32 pos = s[k] == 0 ? n - 1 : s[k] - 1;
+        b[k] = (j0 + k < n) ? (u32)__ldg(text + pos) : 0u;
+        if (s[k] == 0 && j0 + k < n) *origin = j0 + k;
+    }
+    if (j0 + 4 <= n && bwt_aligned4) {
+        *reinterpret_cast<u32*>(bwt + j0) = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (j0 + k < n) bwt[j0 + k] = (u8)b[k];
+    }
+}
+
+// ---- verification (independent of the construction kernels) ------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_verify_scatter(const u32* __restrict__ sa, u32 n, u32* __restrict__ isa, unsigned long long* bad) {
+    const u64 j = (u64)blockIdx.x * THREADS + threadIdx.x;
+    if (j >= n) return;
+    const u32 v = sa[j];
+    if (v >= n) atomicAdd(bad, 1ull);
+    else isa[v] = (u32)j;
+}
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_verify_order(const u8* __restrict__ text, const u32* __restrict__ sa, u32 n, const u32* __restrict__ isa, unsigned long long* bad) {
+    const u64 j = (u64)blockIdx.x * THREADS + threadIdx.x;
+    if (j >= n) return;
+    const u32 b = sa[j];
+    if (b >= n) return;  // counted by the scatter kernel
+    bool ok = isa[b] == (u32)j;  // permutation: every value hit exactly once
+    if (ok && j > 0) {
+        const u32 a = sa[j - 1];
+        if (a >= n) return;
+        const u8 ta = text[a], tb = text[b];
+        if (ta > tb) ok = false;
+        else if (ta == tb) {
+            const long long ra = ((u64)a + 1 < n) ? (long long)isa[a + 1] : -1;
+            const long long rb = ((u64)b + 1 < n) ? (long long)isa[b + 1] : -1;
+            ok = ra < rb;
+        }
+    }
+    if (!ok) atomicAdd(bad, 1ull);
+}
+
+}  // namespace dark

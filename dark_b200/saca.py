@@ -1,0 +1,154 @@
+"""Host-side mirror of the reference's `saca` module (src/saca.rs) over the C ABI.
+
+Same names, argument meaning and error behaviour as the Rust original so that the parity
+tests read like the reference's own (`saca::test::some_detail`, src/saca.rs:393-407):
+
+    Symbol = u8, Suffix = u32, SUF_INVALID = !0          src/saca.rs:18-22
+    Constructor::new(max_n)                               src/saca.rs:351-360
+    Constructor::capacity()                               src/saca.rs:363-365
+    Constructor::compute(input) -> &[Suffix]              src/saca.rs:368-378   (asserts len == capacity)
+    Constructor::reuse() -> &mut [Suffix]                 src/saca.rs:381-383
+plus the fused entry the two call sites use instead of compute + TransformIterator
+(src/block/dc.rs:45-50, src/block/raw.rs:39-44):
+    Constructor::bwt(input) -> (Vec<u8>, usize)
+
+Errors raise DarkBwtError where the Rust code panics (wrong length: saca.rs:369; n < 2:
+saca.rs:69/300).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _ffi
+
+Symbol = np.uint8
+Suffix = np.uint32
+SUF_INVALID = 0xFFFFFFFF
+
+
+def _as_u8(buf):
+    if isinstance(buf, np.ndarray):
+        return np.ascontiguousarray(buf, dtype=np.uint8)
+    return np.frombuffer(bytes(buf) if not isinstance(buf, (bytes, bytearray, memoryview)) else buf, dtype=np.uint8)
+
+
+class Constructor:
+    """Suffix Array Constructor (GPU).  Not thread-safe, like `&mut self` in the reference."""
+
+    def __init__(self, max_n, device=0, flags=_ffi.F_DEFAULT):
+        self._L = _ffi.lib()
+        self._ctx = ctypes.c_void_p()
+        _ffi.check(self._L.dark_bwt_create_ex(int(max_n), int(device), int(flags), ctypes.byref(self._ctx)),
+                   None, "Constructor::new")
+        self.n = int(max_n)
+        self.device = int(device)
+        self.stats = _ffi.Stats()
+
+    # -- reference API --------------------------------------------------------------------
+    def capacity(self):
+        return int(self._L.dark_bwt_capacity(self._ctx))
+
+    def compute(self, input):
+        """Suffix array of `input` (np.uint32[n]).  `len(input)` must equal capacity (saca.rs:369)."""
+        t = _as_u8(input)
+        if t.size != self.n:
+            raise _ffi.DarkBwtError(_ffi.E_INVALID_N, f"assertion failed: input.len() == self.n ({t.size} != {self.n})")
+        _, _, sa = self._forward(t, want_sa=True)
+        return sa
+
+    def reuse(self):
+        """The context's host scratch as np.uint32 (>= capacity words; n + extra like saca.rs:353-357)."""
+        p, cnt = ctypes.c_void_p(), ctypes.c_uint64()
+        _ffi.check(self._L.dark_bwt_reuse(self._ctx, ctypes.byref(p), ctypes.byref(cnt)), self._ctx, "reuse")
+        buf = (ctypes.c_uint32 * cnt.value).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.uint32)
+
+    # -- the fused call-site entry -----------------------------------------------------------
+    def bwt(self, input):
+        """(BWT bytes np.uint8[n], origin) of a block of up to `capacity` bytes."""
+        out, origin, _ = self._forward(_as_u8(input), want_sa=False)
+        return out, origin
+
+    def bwt_and_sa(self, input):
+        return self._forward(_as_u8(input), want_sa=True)
+
+    def _forward(self, t, want_sa):
+        out = np.empty(t.size, dtype=np.uint8)
+        sa = np.empty(t.size, dtype=np.uint32) if want_sa else None
+        origin = ctypes.c_uint64(0)
+        rc = self._L.dark_bwt_forward(self._ctx, t.ctypes.data if t.size else None, t.size, out.ctypes.data if t.size else None,
+                                      ctypes.byref(origin), sa.ctypes.data if (want_sa and t.size) else None,
+                                      ctypes.byref(self.stats))
+        if rc == _ffi.E_INVALID_ARG and t.size == 0:
+            rc = _ffi.E_INVALID_N
+        _ffi.check(rc, self._ctx, "Constructor::bwt")
+        return out, int(origin.value), sa
+
+    def bwt_into(self, text_ptr, n, bwt_ptr, sa_ptr=None):
+        """Host-buffer entry on raw addresses (e.g. pinned buffers): returns origin."""
+        origin = ctypes.c_uint64(0)
+        _ffi.check(self._L.dark_bwt_forward(self._ctx, text_ptr, int(n), bwt_ptr, ctypes.byref(origin), sa_ptr,
+                                            ctypes.byref(self.stats)), self._ctx, "Constructor::bwt")
+        return int(origin.value)
+
+    # -- device-resident form (benches, pipelines that keep the block in HBM) ------------------
+    def bwt_device(self, d_text, n, d_bwt, d_sa=None):
+        """Raw device pointers (ints).  Returns origin; self.stats holds the device timings."""
+        origin = ctypes.c_uint64(0)
+        _ffi.check(self._L.dark_bwt_forward_device(self._ctx, d_text, int(n), d_bwt, ctypes.byref(origin), d_sa,
+                                                   ctypes.byref(self.stats)), self._ctx, "Constructor::bwt_device")
+        return int(origin.value)
+
+    def verify_sa_device(self, d_text, n, d_sa):
+        bad = ctypes.c_uint64(0)
+        _ffi.check(self._L.dark_bwt_verify_sa_device(self._ctx, d_text, int(n), d_sa, ctypes.byref(bad)), self._ctx,
+                   "verify_sa")
+        return int(bad.value)
+
+    def emit_device(self, d_text, n, d_sa, d_bwt):
+        origin = ctypes.c_uint64(0)
+        _ffi.check(self._L.dark_bwt_emit_device(self._ctx, d_text, int(n), d_sa, d_bwt, ctypes.byref(origin)), self._ctx,
+                   "emit")
+        return int(origin.value)
+
+    def sort_pairs_device(self, d_keys, d_vals, d_keys_alt, d_vals_alt, count, begin_bit=0, end_bit=64):
+        in_alt, ms = ctypes.c_int(0), ctypes.c_float(0)
+        _ffi.check(self._L.dark_bwt_sort_pairs_device(self._ctx, d_keys, d_vals, d_keys_alt, d_vals_alt, int(count),
+                                                      begin_bit, end_bit, ctypes.byref(in_alt), ctypes.byref(ms)),
+                   self._ctx, "sort_pairs")
+        return bool(in_alt.value), float(ms.value)
+
+    @property
+    def stream(self):
+        return self._L.dark_bwt_stream(self._ctx)
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._L.dark_bwt_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def transform(input, suf):
+    """`compress::bwt::TransformIterator::new(input, suf)` collected: (bytes, origin).
+
+    Host-side numpy statement of the emission rule, kept for callers that already hold a
+    suffix array (the reference's tests do this, saca.rs:398-400).  The hot path uses
+    Constructor.bwt, which never materialises the SA on the host."""
+    t = _as_u8(input)
+    s = np.asarray(suf, dtype=np.uint32)
+    n = t.size
+    idx = (s.astype(np.int64) + n - 1) % n
+    origin = int(np.flatnonzero(s == 0)[0])
+    return t[idx], origin

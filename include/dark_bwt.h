@@ -1,0 +1,155 @@
+/*
+ * dark_bwt.h — C ABI of the B200-native forward Burrows–Wheeler transform that replaces
+ * kvark/dark's `saca::Constructor::compute` + `compress::bwt::TransformIterator`.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, nothing
+ * unwinds across it.  A Rust `-sys` crate binds exactly these symbols (INTEGRATION.md
+ * shows the binding and the 6-line patch to src/block/{dc,raw}.rs).
+ *
+ * Reference interface each entry point replaces (paths under /root/reference):
+ *
+ *   dark_bwt_create        saca::Constructor::new(max_n)            src/saca.rs:351-360
+ *   dark_bwt_capacity      Constructor::capacity()                  src/saca.rs:363-365
+ *   dark_bwt_forward       Constructor::compute(input) followed by  src/saca.rs:368-378
+ *                          bwt::TransformIterator::new(input, suf)
+ *                          .collect() / .get_origin()               src/block/dc.rs:45-50
+ *                                                                   src/block/raw.rs:39-44
+ *   dark_bwt_reuse         Constructor::reuse()                     src/saca.rs:381-383
+ *   dark_bwt_destroy       Drop of Constructor
+ *   dark_bwt_strerror      text of the panic the Rust wrapper raises (assert!s at
+ *                          src/saca.rs:272,300,369)
+ *
+ * Semantics (bit-exact with the reference):
+ *   SA   = the permutation of 0..n-1 sorting the suffixes T[i..n) as byte strings,
+ *          a proper prefix sorting first (virtual end-of-text below every byte);
+ *   bwt[i] = T[SA[i]-1], except at the one i with SA[i]==0 where bwt[i] = T[n-1]
+ *          and origin = i (known-answer test src/saca.rs:409-413).
+ *   Suffix = uint32_t (src/saca.rs:20), so 2 <= n <= 2^32-2; n < 2 is an error because
+ *   the reference panics there (n==0: src/saca.rs:69, n==1: src/saca.rs:300).
+ *
+ * Threading: a context is NOT thread-safe (the reference's `&mut self`); distinct
+ * contexts are independent — one per GPU per host thread.  Every call selects the
+ * context's device itself.  There is no CPU fallback: without a usable CUDA device
+ * dark_bwt_create fails with DARK_BWT_E_CUDA.
+ */
+#ifndef DARK_BWT_H
+#define DARK_BWT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DARK_BWT_ABI_VERSION 1
+
+/* error codes (0 = ok) */
+#define DARK_BWT_OK 0
+#define DARK_BWT_E_INVALID_N 1   /* n < 2, n > capacity, or n > 2^32-2                       */
+#define DARK_BWT_E_INVALID_ARG 2 /* null pointer / bad device / bad flags                    */
+#define DARK_BWT_E_CUDA 3        /* a CUDA call failed; dark_bwt_last_error() has the text    */
+#define DARK_BWT_E_NOMEM 4       /* device or pinned-host allocation failed at create        */
+#define DARK_BWT_E_INTERNAL 5    /* invariant violated (should not happen; reported, not UB) */
+
+/* flags for dark_bwt_create_ex */
+#define DARK_BWT_F_DEFAULT 0u
+/* Canonical mode of SURVEY.md §8(d): 8 raw bytes per initial key (no alphabet packing), so
+ * the per-round active counts equal the oracle profiler's m_r.  Results are identical. */
+#define DARK_BWT_F_NO_ALPHABET_PACKING 1u
+/* Do not allocate the host-entry staging (device text/BWT/SA-out buffers, pinned memory):
+ * for callers that only use dark_bwt_forward_device. */
+#define DARK_BWT_F_DEVICE_ONLY 2u
+
+#define DARK_BWT_MAX_ROUNDS 40
+
+typedef struct dark_bwt_ctx dark_bwt_ctx;
+
+/* Filled by the forward calls when `stats` is non-null.  Times are CUDA-event times on the
+ * context's stream (milliseconds). */
+typedef struct dark_bwt_stats {
+    uint64_t n;
+    uint32_t sigma;           /* distinct byte values in the block                        */
+    uint32_t bits_per_symbol; /* s                                                        */
+    uint32_t symbols_per_key; /* K: symbols packed into the initial 64-bit key            */
+    uint32_t rounds;          /* prefix-doubling rounds after the initial sort            */
+    uint32_t sort_passes;     /* radix-pass kernel launches, all rounds                   */
+    uint32_t kernel_launches; /* every kernel this call launched                          */
+    uint64_t active[DARK_BWT_MAX_ROUNDS]; /* [0] = n; [r] = unsettled suffixes entering round r */
+    uint32_t passes[DARK_BWT_MAX_ROUNDS]; /* radix passes run in round r (0 = initial sort)     */
+    uint64_t sorted_elements; /* sum over pass launches of the elements each one moved    */
+    float device_ms;          /* whole forward: first kernel -> BWT + origin in HBM       */
+    float init_ms;            /* alphabet scan + initial key build                        */
+    float sort_ms;            /* histogram scan + radix-pass kernels (incl. host round trip) */
+    float pass_ms;            /* radix-pass kernels alone (with their status memsets)     */
+    float keybuild_ms;        /* (rank[i], rank[i+h]) key construction                    */
+    float rerank_ms;          /* re-rank + compaction scans                               */
+    float emit_ms;            /* BWT gather + origin                                      */
+    float h2d_ms;             /* host entry point only                                    */
+    float d2h_ms;             /* host entry point only                                    */
+} dark_bwt_stats;
+
+/* Constructor::new — allocates every device buffer for blocks of up to max_n bytes on
+ * CUDA device `device` (about 38.5 * max_n bytes of HBM).  Nothing is allocated later. */
+int dark_bwt_create(uint64_t max_n, int device, dark_bwt_ctx **out);
+int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx **out);
+
+/* Constructor::capacity */
+uint64_t dark_bwt_capacity(const dark_bwt_ctx *ctx);
+
+/* compute + TransformIterator on HOST buffers: text[0..n) -> bwt_out[0..n), *origin_out,
+ * and, if sa_out is non-null, the suffix array sa_out[0..n).  Pinned host buffers are
+ * copied directly; pageable ones through the context's pinned staging.  `stats` nullable. */
+int dark_bwt_forward(dark_bwt_ctx *ctx, const uint8_t *text, uint64_t n, uint8_t *bwt_out, uint64_t *origin_out,
+                     uint32_t *sa_out, dark_bwt_stats *stats);
+
+/* Same on DEVICE buffers (d_text, d_bwt_out, d_sa_out live on the context's device;
+ * d_sa_out nullable; origin_out and stats are host pointers).  No readable slack after
+ * d_text[n-1] is required.  Returns after the work has completed on the stream. */
+int dark_bwt_forward_device(dark_bwt_ctx *ctx, const uint8_t *d_text, uint64_t n, uint8_t *d_bwt_out,
+                            uint64_t *origin_out, uint32_t *d_sa_out, dark_bwt_stats *stats);
+
+/* Constructor::reuse — lends >= capacity host u32 words of scratch (DC distances in
+ * block/dc.rs:51).  Allocated on first use; owned by the context. */
+int dark_bwt_reuse(dark_bwt_ctx *ctx, uint32_t **words_out, uint64_t *count_out);
+
+void dark_bwt_destroy(dark_bwt_ctx *ctx);
+
+const char *dark_bwt_strerror(int code);
+/* Text of the last CUDA/internal failure on this context ("" if none). */
+const char *dark_bwt_last_error(const dark_bwt_ctx *ctx);
+
+/* The CUDA stream (cudaStream_t) all of this context's work is launched on, so a harness
+ * can bracket calls with its own events. */
+void *dark_bwt_stream(const dark_bwt_ctx *ctx);
+
+int dark_bwt_abi_version(void);
+
+/* ---- building blocks, exported for unit tests, verification and benches ------------------ */
+
+/* LSD radix sort of (u64 key, u32 value) pairs on bits [begin_bit, end_bit) with the
+ * context's onesweep passes.  d_keys/d_vals hold the input; d_keys_alt/d_vals_alt are
+ * scratch of the same size.  *in_alt_out = 1 if the sorted data ended in the alt buffers.
+ * count <= capacity. */
+int dark_bwt_sort_pairs_device(dark_bwt_ctx *ctx, uint64_t *d_keys, uint32_t *d_vals, uint64_t *d_keys_alt,
+                               uint32_t *d_vals_alt, uint64_t count, int begin_bit, int end_bit, int *in_alt_out,
+                               float *ms_out);
+
+/* O(n) device check that d_sa is the suffix array of d_text (permutation; then for every j:
+ * T[SA[j]] < T[SA[j+1]], or equal and ISA[SA[j]+1] < ISA[SA[j+1]+1], end-of-text lowest).
+ * *bad_out = number of violations (0 = correct). Independent of the construction kernels. */
+int dark_bwt_verify_sa_device(dark_bwt_ctx *ctx, const uint8_t *d_text, uint64_t n, const uint32_t *d_sa,
+                              uint64_t *bad_out);
+
+/* BWT emission alone: bwt[i] = T[SA[i]-1] / origin, from a device SA. */
+int dark_bwt_emit_device(dark_bwt_ctx *ctx, const uint8_t *d_text, uint64_t n, const uint32_t *d_sa,
+                         uint8_t *d_bwt_out, uint64_t *origin_out);
+
+/* Synthetic block generators of SURVEY.md App. D on the host ("dna", "rep17", "text",
+ * "mixed").  Returns DARK_BWT_E_INVALID_ARG for an unknown kind. */
+int dark_bwt_synth(const char *kind, uint64_t seed, uint8_t *out, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DARK_BWT_H */

@@ -1,0 +1,284 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI
+(dark_b200.saca.Constructor -> libdark_bwt.so), against the CPU oracle and the committed
+golden fixtures.  Integer work: every comparison is bit-exact.
+
+They mirror the reference's own tests: saca::test::detailed / roundtrips
+(/root/reference/src/saca.rs:409-433) plus the differential and edge cases of SURVEY.md §4 (T1-T4).
+"""
+import ctypes
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def crc(a):
+    return "%08x" % (zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xFFFFFFFF)
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    if not t.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (there is no CPU fallback for the forward BWT)")
+    return t
+
+
+@pytest.fixture(scope="module")
+def saca():
+    from dark_b200 import saca as s
+    return s
+
+
+@pytest.fixture(scope="module")
+def con_small(saca, torch):
+    c = saca.Constructor(1 << 16)
+    yield c
+    c.close()
+
+
+def run_both_modes(saca, text):
+    """(bwt, origin, sa) in default mode and in canonical (no alphabet packing) mode."""
+    from dark_b200 import _ffi
+    res = []
+    for flags in (_ffi.F_DEFAULT, _ffi.F_NO_ALPHABET_PACKING):
+        with saca.Constructor(len(text), flags=flags) as c:
+            res.append(c.bwt_and_sa(text) + (c.stats.as_dict(),))
+    return res
+
+
+# ---- the reference's known answers: saca.rs:411-412 -------------------------------------------
+KAT = [
+    (b"abracadabra", [10, 7, 0, 3, 5, 8, 1, 4, 6, 9, 2], 2, b"rdarcaaaabb"),
+    (b"banana", [5, 3, 1, 0, 4, 2], 3, b"nnbaaa"),
+]
+
+
+@pytest.mark.parametrize("text,sa_exp,origin_exp,bwt_exp", KAT)
+def test_reference_known_answers(saca, oracle, torch, text, sa_exp, origin_exp, bwt_exp):
+    # some_detail(): Constructor::new(len) -> compute -> TransformIterator -> decode (saca.rs:393-407)
+    con = saca.Constructor(len(text))
+    suf = con.compute(text)
+    assert suf.tolist() == sa_exp
+    out, origin = saca.transform(text, suf)
+    assert origin == origin_exp and out.tobytes() == bwt_exp
+    out2, origin2 = con.bwt(text)           # the fused call-site entry
+    assert origin2 == origin_exp and out2.tobytes() == bwt_exp
+    scratch = con.reuse()
+    assert scratch.size >= len(text)
+    assert oracle.bwt_decode(out2, origin2).tobytes() == text
+    con.close()
+
+
+def test_error_behaviour_matches_reference_panics(saca, torch):
+    from dark_b200 import DarkBwtError
+    con = saca.Constructor(16)
+    assert con.capacity() == 16
+    with pytest.raises(DarkBwtError):       # assert_eq!(input.len(), self.n)  saca.rs:369
+        con.compute(b"too short")
+    with pytest.raises(DarkBwtError):       # n == 1: assert at saca.rs:300
+        con.bwt(b"x")
+    with pytest.raises(DarkBwtError):       # n == 0: input[1..] panics, saca.rs:69
+        con.bwt(b"")
+    with pytest.raises(DarkBwtError):       # block larger than capacity: block/dc.rs:43
+        con.bwt(b"y" * 17)
+    out, origin = con.bwt(b"ba")            # smallest legal block, below capacity: SA = [1, 0]
+    assert (out.tobytes(), origin) == (b"ba", 1)
+    con.close()
+    with pytest.raises(DarkBwtError):
+        saca.Constructor(1)
+
+
+# ---- differential against the oracle on small inputs ------------------------------------------
+@pytest.mark.parametrize("sigma", [1, 2, 3, 4, 26, 256])
+def test_small_random_differential(con_small, oracle, sigma):
+    rng = np.random.default_rng(2000 + sigma)
+    for it in range(60):
+        n = int(rng.integers(2, 70)) if it < 40 else int(rng.integers(70, 9000))
+        lo = int(rng.integers(0, 257 - sigma))
+        t = (rng.integers(0, sigma, n) + lo).astype(np.uint8)
+        bwt, origin, sa = con_small.bwt_and_sa(t)
+        sa_o = oracle.saca(t)
+        assert np.array_equal(sa, sa_o), (sigma, n, t[:80].tolist())
+        bwt_o, origin_o = oracle.bwt_emit(t, sa_o)
+        assert origin == origin_o and np.array_equal(bwt, bwt_o)
+
+
+EDGE = [
+    bytes([0, 0]), bytes([0, 1]), bytes([1, 0]), bytes([255, 255, 255]), bytes([0, 255, 0]),
+    b"\x00" * 100, b"\xff" * 100, b"\x00" * 4097, b"ab" * 50, b"ab" * 50 + b"a", (b"abc" * 40)[:-1],
+    b"a" * 63 + b"b", b"b" + b"a" * 63, bytes(range(256)), bytes(range(255, -1, -1)),
+    b"\x00\x00\x00\x01\x00\x00\x00", b"aaaaaaaab" * 7 + b"aaaaaaaa", b"\x00" * 7 + b"\x01" + b"\x00" * 9,
+    (b"oxvkjttpuoovephyk" * 300), (b"oxvkjttpuoovephyk" * 300)[:4099], b"ACGT" * 1025, b"A" * 5000 + b"C",
+    bytes(range(256)) * 17,
+]
+
+
+@pytest.mark.parametrize("idx", range(len(EDGE)))
+def test_edge_cases_both_modes(saca, oracle, torch, idx):
+    # no in-band sentinel (0x00 and 0xFF are ordinary symbols), periodic tails, all-equal bytes,
+    # n not a multiple of any tile
+    t = EDGE[idx]
+    sa_o = oracle.saca(t)
+    bwt_o, origin_o = oracle.bwt_emit(t, sa_o)
+    for bwt, origin, sa, _ in run_both_modes(saca, t):
+        assert np.array_equal(sa, sa_o)
+        assert origin == origin_o and np.array_equal(bwt, bwt_o)
+
+
+# ---- medium: the App. D shapes, direct comparison + committed fixtures ------------------------
+MEDIUM = ["text:3:768771", "dna:1:65536", "dna:1:1048576", "dna:7:1060921", "rep17:2:65536", "rep17:2:1048576",
+          "rep17:2:4194304", "mixed:4:1048576", "mixed:1000:4194304", "text:5:100003"]
+
+
+@pytest.mark.parametrize("key", MEDIUM)
+def test_medium_shapes_vs_oracle_and_fixtures(saca, oracle, golden, torch, key):
+    from dark_b200 import synth
+    kind, seed, n = key.split(":")
+    t = synth.generate(kind, int(seed), int(n))
+    g = golden[key]
+    assert crc(t) == g["text_crc32"]
+    bwt_o, origin_o, sa_o = oracle.bwt_forward(t, want_sa=True)
+    (bwt, origin, sa, st), (bwt2, origin2, sa2, st2) = run_both_modes(saca, t)
+    assert np.array_equal(sa, sa_o) and np.array_equal(sa2, sa_o)
+    assert origin == origin_o == origin2 == g["origin"]
+    assert np.array_equal(bwt, bwt_o) and np.array_equal(bwt2, bwt_o)
+    assert crc(bwt) == g["bwt_crc32"] and crc(sa) == g["sa_crc32"]
+    # canonical mode (8 bytes per initial key): the per-round active counts are the profiler's m_r
+    assert st2["symbols_per_key"] == 8
+    assert st2["active"][1:] == g["profile"]["m"], (st2["active"], g["profile"]["m"])
+    assert st2["rounds"] == g["profile"]["R"]
+    # round trip like saca.rs:415-427
+    assert np.array_equal(oracle.bwt_decode(bwt, origin), t)
+
+
+def test_u64_status_path_small(oracle):
+    """The 64-bit tile-status variant of the radix pass (used for sorts of >= 2^30 pairs, i.e. the
+    2 GiB block) forced on a small input in a fresh process."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, oracle\n"
+        "from dark_b200 import saca, synth\n"
+        "t = synth.generate('mixed', 4, 300001)\n"
+        "c = saca.Constructor(t.size)\n"
+        "b, o, s = c.bwt_and_sa(t)\n"
+        "bo, oo, so = oracle.bwt_forward(t, want_sa=True)\n"
+        "assert o == oo and np.array_equal(b, bo) and np.array_equal(s, so)\n"
+        "print('ok')\n")
+    env = dict(os.environ, DARK_BWT_FORCE_U64_STATUS="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+# ---- building blocks -------------------------------------------------------------
+@pytest.mark.parametrize("m,begin,end", [(1, 0, 64), (100, 0, 64), (4096, 0, 64), (4097, 0, 64), (1000003, 0, 64),
+                                         (300000, 0, 40), (300000, 16, 48), (50000, 0, 8)])
+def test_radix_sort_pairs_is_a_stable_sort(saca, torch, m, begin, end):
+    rng = np.random.default_rng(m + begin)
+    keys = rng.integers(0, 1 << 63, m, dtype=np.uint64) * 2 + rng.integers(0, 2, m, dtype=np.uint64)
+    if m > 1000:
+        keys[: m // 2] &= np.uint64(0x00FF00FF00FF00FF)      # skewed digits, many ties
+    vals = np.arange(m, dtype=np.uint32)
+    con = saca.Constructor(max(m, 2))
+    dk = torch.from_numpy(keys.view(np.int64)).cuda()
+    dv = torch.from_numpy(vals.view(np.int32)).cuda()
+    dk2, dv2 = torch.empty_like(dk), torch.empty_like(dv)
+    in_alt, _ = con.sort_pairs_device(dk.data_ptr(), dv.data_ptr(), dk2.data_ptr(), dv2.data_ptr(), m, begin, end)
+    torch.cuda.synchronize()
+    rk = (dk2 if in_alt else dk).cpu().numpy().view(np.uint64)
+    rv = (dv2 if in_alt else dv).cpu().numpy().view(np.uint32)
+    nbits = end - begin
+    passes = (nbits + 7) // 8
+    mask = np.uint64((1 << min(64 - begin, passes * 8)) - 1)
+    sub = (keys >> np.uint64(begin)) & mask                   # whole 8-bit digits take part
+    order = np.argsort(sub, kind="stable")
+    assert np.array_equal(rv, vals[order])
+    assert np.array_equal(rk, keys[order])
+    con.close()
+
+
+def test_emission_kernel_alone(saca, oracle, torch):
+    from dark_b200 import synth
+    for n in (2, 3, 5, 1023, 100003):
+        t = synth.generate("text", 11, n)
+        sa = oracle.saca(t)
+        bwt_o, origin_o = oracle.bwt_emit(t, sa)
+        con = saca.Constructor(n)
+        dt = torch.from_numpy(t.copy()).cuda()
+        ds = torch.from_numpy(sa.view(np.int32)).cuda()
+        for off in (0, 1):                                    # aligned and unaligned output pointer
+            db = torch.zeros(n + 8, dtype=torch.uint8, device="cuda")
+            origin = con.emit_device(dt.data_ptr(), n, ds.data_ptr(), db.data_ptr() + off)
+            assert origin == origin_o
+            assert np.array_equal(db.cpu().numpy()[off:off + n], bwt_o)
+        con.close()
+
+
+def test_gpu_verifier_accepts_and_rejects(saca, oracle, torch):
+    from dark_b200 import synth
+    t = synth.generate("mixed", 9, 200001)
+    sa = oracle.saca(t)
+    con = saca.Constructor(t.size)
+    dt = torch.from_numpy(t.copy()).cuda()
+    ds = torch.from_numpy(sa.view(np.int32)).cuda()
+    assert con.verify_sa_device(dt.data_ptr(), t.size, ds.data_ptr()) == 0
+    bad = sa.copy()
+    bad[[1000, 1001]] = bad[[1001, 1000]]
+    ds = torch.from_numpy(bad.view(np.int32)).cuda()
+    assert con.verify_sa_device(dt.data_ptr(), t.size, ds.data_ptr()) > 0
+    bad = sa.copy()
+    bad[5] = bad[6]                                           # not a permutation
+    ds = torch.from_numpy(bad.view(np.int32)).cuda()
+    assert con.verify_sa_device(dt.data_ptr(), t.size, ds.data_ptr()) > 0
+    con.close()
+
+
+# ---- large: fixtures + the independent GPU verifier ---------------------------
+LARGE = ["dna:1:16777216", "mixed:4:16777216", "rep17:2:67108864", "dna:1:268435456", "mixed:1000:268435456"]
+
+
+@pytest.mark.parametrize("key", LARGE)
+def test_large_shapes_vs_fixtures_device_resident(saca, golden, torch, key):
+    """C2 (256 MB DNA), C3 (64 MB period-17), a C5 block, device-resident through
+    dark_bwt_forward_device; SA checked by the O(n) GPU verifier, BWT/SA/origin by CRC against
+    the oracle's committed outputs."""
+    from dark_b200 import synth, _ffi
+    kind, seed, n = key.split(":")
+    n = int(n)
+    g = golden[key]
+    t = synth.generate(kind, int(seed), n)
+    assert crc(t) == g["text_crc32"]
+    con = saca.Constructor(n, flags=_ffi.F_DEVICE_ONLY)
+    dt = torch.from_numpy(t).cuda()
+    db = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ds = torch.empty(n, dtype=torch.int32, device="cuda")
+    origin = con.bwt_device(dt.data_ptr(), n, db.data_ptr(), ds.data_ptr())
+    st = con.stats.as_dict()
+    assert origin == g["origin"]
+    assert con.verify_sa_device(dt.data_ptr(), n, ds.data_ptr()) == 0
+    assert crc(db.cpu().numpy()) == g["bwt_crc32"]
+    assert crc(ds.cpu().numpy()) == g["sa_crc32"]
+    # without the SA output buffer the result is the same
+    db2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    assert con.bwt_device(dt.data_ptr(), n, db2.data_ptr(), None) == origin
+    assert torch.equal(db, db2)
+    print(key, {k: st[k] for k in ("sigma", "symbols_per_key", "rounds", "sort_passes", "device_ms")})
+    con.close()
+
+
+def test_idempotent_context_reuse(saca, oracle, torch):
+    """One context, many blocks of different sizes (the Encoder keeps its Constructor)."""
+    from dark_b200 import synth
+    con = saca.Constructor(1 << 20)
+    for kind, seed, n in (("dna", 3, 1 << 20), ("text", 4, 12345), ("rep17", 5, 999999), ("mixed", 6, 1 << 19),
+                          ("dna", 3, 1 << 20)):
+        t = synth.generate(kind, seed, n)
+        bwt, origin = con.bwt(t)
+        bwt_o, origin_o = oracle.bwt_forward(t)
+        assert origin == origin_o and np.array_equal(bwt, bwt_o)
+    con.close()
