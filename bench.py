@@ -141,7 +141,7 @@ def run_native(args, rank, local_rank, world):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from dark_b200 import saca, synth
+    from dark_b200 import saca, synth, blocks
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the forward BWT has no CPU fallback")
@@ -202,18 +202,15 @@ def run_native(args, rank, local_rank, world):
     assert origin_h == origin
     assert torch.equal(h_bwt[: 1 << 20], d_bwt[: 1 << 20].cpu())
 
-    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ln = torch.tensor([launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
-        launches = int(ln.item())
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    # max over ranks of the time, sum over ranks of the work (dark_b200.blocks.aggregate; gloo-tested)
+    ms_total, total_bytes = blocks.aggregate(ms_total, n * args.steps)
+    e2e_ms, e2e_bytes = blocks.aggregate(e2e_s * 1e3, n * e2e_steps)
+    _, launches = blocks.aggregate(0.0, launches)
 
     if rank == 0:
         ms_per_step = ms_total / args.steps
-        value = world * n / 1e6 / (ms_per_step / 1e3)
-        e2e_value = world * n * e2e_steps / 1e6 / (e2e_ms / 1e3)
+        value = total_bytes / 1e6 / (ms_total / 1e3)
+        e2e_value = e2e_bytes / 1e6 / (e2e_ms / 1e3)
         peak, peak_src = measured_peak_gbs()
         pass_gbs = 24.0 * agg["sorted"] / (agg["pass_ms"] / 1e3) / 1e9 if agg["pass_ms"] > 0 else 0.0
         path_gbs = balg_per_byte * n / (ms_per_step / 1e3) / 1e9

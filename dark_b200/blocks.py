@@ -21,3 +21,19 @@ def bwt_blocks(constructor, blocks):
     """Run the forward BWT over an iterable of host blocks on one context; yields (bwt, origin)."""
     for blk in blocks:
         yield constructor.bwt(blk)
+
+
+def aggregate(ms_local, units_local, group=None):
+    """(max over ranks of the device time, sum over ranks of the units processed) — the reduction
+    behind the multi-GPU throughput.  Works on any torch.distributed backend (NCCL on the GPU box,
+    gloo in the CPU tests); a single process returns its own numbers."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(ms_local), int(units_local)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.tensor([float(ms_local)], dtype=torch.float64, device=dev)
+    u = torch.tensor([int(units_local)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM, group=group)
+    return float(t.item()), int(u.item())
