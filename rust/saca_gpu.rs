@@ -1,0 +1,86 @@
+/*!
+Drop-in replacement for the body of `src/saca.rs` of kvark/dark: same public items
+(`Symbol`, `Suffix`, `Constructor::{new, capacity, compute, reuse}`), backed by the
+B200-native library through `dark-bwt-sys`, plus `Constructor::bwt` for the two call
+sites.  UNCOMPILED in this image (no Rust toolchain) — deliberately thin.
+
+Errors panic, which is the reference's convention (assert!s at saca.rs:272,300,369).
+*/
+extern crate dark_bwt_sys as sys;
+
+use std::ffi::CStr;
+use std::{ptr, slice};
+
+/// Symbol type
+pub type Symbol = u8;
+/// Suffix type = index of the original sub-string
+pub type Suffix = u32;
+
+/// Suffix Array Constructor (GPU)
+pub struct Constructor {
+    ctx: *mut sys::dark_bwt_ctx,
+    n: usize,
+    sa: Vec<Suffix>,   // host copy handed out by compute()
+    out: Vec<Symbol>,
+}
+
+fn check(ctx: *const sys::dark_bwt_ctx, rc: i32, what: &str) {
+    if rc != sys::DARK_BWT_OK {
+        let msg = unsafe { CStr::from_ptr(sys::dark_bwt_strerror(rc)) }.to_string_lossy().into_owned();
+        let detail = if ctx.is_null() { String::new() } else {
+            unsafe { CStr::from_ptr(sys::dark_bwt_last_error(ctx)) }.to_string_lossy().into_owned()
+        };
+        panic!("{}: {} {}", what, msg, detail);
+    }
+}
+
+impl Constructor {
+    /// Create a new instance for a given maximum input size
+    pub fn new(max_n: usize) -> Constructor {
+        let mut ctx = ptr::null_mut();
+        let rc = unsafe { sys::dark_bwt_create(max_n as u64, 0, &mut ctx) };
+        check(ctx, rc, "saca::Constructor::new");
+        Constructor { ctx: ctx, n: max_n, sa: Vec::new(), out: Vec::new() }
+    }
+
+    /// Return maximum block size
+    pub fn capacity(&self) -> usize {
+        unsafe { sys::dark_bwt_capacity(self.ctx) as usize }
+    }
+
+    /// Compute the suffix array for a given input
+    pub fn compute<'a>(&'a mut self, input: &[Symbol]) -> &'a [Suffix] {
+        assert_eq!(input.len(), self.n);
+        self.sa.resize(input.len(), 0);
+        self.out.resize(input.len(), 0);
+        let mut origin = 0u64;
+        let rc = unsafe { sys::dark_bwt_forward(self.ctx, input.as_ptr(), input.len() as u64,
+            self.out.as_mut_ptr(), &mut origin, self.sa.as_mut_ptr(), ptr::null_mut()) };
+        check(self.ctx, rc, "saca::Constructor::compute");
+        &self.sa[..]
+    }
+
+    /// BWT bytes and origin of a block: what `compute` + `bwt::TransformIterator` produced
+    pub fn bwt(&mut self, input: &[Symbol]) -> (Vec<Symbol>, usize) {
+        let mut out = vec![0u8; input.len()];
+        let mut origin = 0u64;
+        let rc = unsafe { sys::dark_bwt_forward(self.ctx, input.as_ptr(), input.len() as u64,
+            out.as_mut_ptr(), &mut origin, ptr::null_mut(), ptr::null_mut()) };
+        check(self.ctx, rc, "saca::Constructor::bwt");
+        (out, origin as usize)
+    }
+
+    /// Temporarily provide the storage for outside needs
+    pub fn reuse<'a>(&'a mut self) -> &'a mut [Suffix] {
+        let (mut p, mut cnt) = (ptr::null_mut(), 0u64);
+        let rc = unsafe { sys::dark_bwt_reuse(self.ctx, &mut p, &mut cnt) };
+        check(self.ctx, rc, "saca::Constructor::reuse");
+        unsafe { slice::from_raw_parts_mut(p, cnt as usize) }
+    }
+}
+
+impl Drop for Constructor {
+    fn drop(&mut self) {
+        unsafe { sys::dark_bwt_destroy(self.ctx) }
+    }
+}
