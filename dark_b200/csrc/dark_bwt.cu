@@ -29,7 +29,7 @@ namespace {
 
 constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;
-constexpr int kSortTile = kSortThreads * kSortItems;
+constexpr int kSortTile = 3072;  // smallest tile of any pass variant (sizes the status buffer)
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
@@ -160,31 +160,55 @@ int next_counter(dark_bwt_ctx* ctx, u32** out) {
     return 0;
 }
 
+// Tuning variants of the radix pass (threads, items per thread, min CTAs per SM).  The default is
+// chosen from measurements (profiles/); DARK_BWT_SORT_VARIANT=<i> selects another one for sweeps.
+template <int THREADS, int ITEMS, int MINBLOCKS>
+int launch_pass_variant(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
+                        const u32* digit_base, u32* counter, bool wide) {
+    typedef OnesweepSmem<THREADS, ITEMS> Smem;
+    const u32 tiles = (u32)ceil_div(m, Smem::kTile);
+    const size_t bytes = (size_t)tiles * kRadix * (wide ? sizeof(u64) : sizeof(u32));
+    if (bytes > ctx->sort_status_bytes) return ctx->fail_internal("sort status buffer too small");
+    CK(cudaMemsetAsync(ctx->sort_status, 0, bytes, ctx->stream));
+    if (!wide) {
+        auto kern = k_onesweep_pass<THREADS, ITEMS, MINBLOCKS, u32>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));  // per device
+        kern<<<tiles, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base,
+                                                            (u32*)ctx->sort_status, counter);
+    } else {
+        auto kern = k_onesweep_pass<THREADS, ITEMS, MINBLOCKS, u64>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));  // per device
+        kern<<<tiles, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base,
+                                                            (u64*)ctx->sort_status, counter);
+    }
+    LAUNCHED();
+    return 0;
+}
+
+constexpr int kDefaultSortVariant = 0;
+
 // One onesweep pass over m pairs: buffers[cur] -> buffers[cur^1].
 int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
                 const u32* digit_base) {
-    typedef OnesweepSmem<kSortThreads, kSortItems> Smem;
-    const u32 tiles = (u32)ceil_div(m, kSortTile);
     u32* counter = nullptr;
     if (int rc = next_counter(ctx, &counter)) return rc;
     // 32-bit status words hold prefixes below 2^30; larger sorts (2 GiB blocks) use 64-bit words.
     // DARK_BWT_FORCE_U64_STATUS=1 exercises the wide path on small inputs (tests).
-    static const bool force64 = getenv("DARK_BWT_FORCE_U64_STATUS") != nullptr;
-    if (m < (1u << 30) && !force64) {
-        const size_t bytes = (size_t)tiles * kRadix * sizeof(u32);
-        if (bytes > ctx->sort_status_bytes) return ctx->fail_internal("sort status buffer too small");
-        CK(cudaMemsetAsync(ctx->sort_status, 0, bytes, ctx->stream));
-        k_onesweep_pass<kSortThreads, kSortItems, u32><<<tiles, kSortThreads, sizeof(Smem), ctx->stream>>>(
-            kin, vin, kout, vout, m, shift, digit_base, (u32*)ctx->sort_status, counter);
-    } else {
-        const size_t bytes = (size_t)tiles * kRadix * sizeof(u64);
-        if (bytes > ctx->sort_status_bytes) return ctx->fail_internal("sort status buffer too small");
-        CK(cudaMemsetAsync(ctx->sort_status, 0, bytes, ctx->stream));
-        k_onesweep_pass<kSortThreads, kSortItems, u64><<<tiles, kSortThreads, sizeof(Smem), ctx->stream>>>(
-            kin, vin, kout, vout, m, shift, digit_base, (u64*)ctx->sort_status, counter);
+    const bool wide = !(m < (1u << 30)) || getenv("DARK_BWT_FORCE_U64_STATUS") != nullptr;
+    const char* ev = getenv("DARK_BWT_SORT_VARIANT");
+    const int variant = ev ? atoi(ev) : kDefaultSortVariant;
+#define V(T, I, B) return launch_pass_variant<T, I, B>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide)
+    switch (variant) {
+        case 1: V(256, 16, 3);
+        case 2: V(512, 8, 2);
+        case 3: V(512, 8, 3);
+        case 4: V(384, 12, 2);
+        case 5: V(512, 12, 2);
+        case 6: V(256, 12, 3);
+        case 7: V(1024, 4, 1);
+        default: V(256, 16, 2);
     }
-    LAUNCHED();
-    return 0;
+#undef V
 }
 
 // Sort passes for a histogram that is already in ctx->hist (counts).  `cur` is the index of the
@@ -316,8 +340,19 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     // ---- round 0: keys of K symbols, ids descending
     {
         const u32 blocks = (u32)ceil_div(n, kInitThreads * kInitItems);
-        k_init_keys<kInitThreads, kInitItems><<<blocks, kInitThreads, 0, ctx->stream>>>(
-            d_text, n, ctx->lut, s_bits, K, ctx->keys[0], ctx->ids[0], ctx->hist, passes0);
+#define INIT_PACKED(S)                                                                                            \
+    k_init_keys_packed<kInitThreads, kInitItems, S><<<blocks, kInitThreads, 0, ctx->stream>>>(d_text, n, ctx->lut, \
+                                                                                              ctx->keys[0], ctx->ids[0], ctx->hist)
+        switch (s_bits) {
+            case 1: INIT_PACKED(1); break;
+            case 2: INIT_PACKED(2); break;
+            case 4: INIT_PACKED(4); break;
+            case 8: INIT_PACKED(8); break;
+            default:
+                k_init_keys<kInitThreads, kInitItems><<<blocks, kInitThreads, 0, ctx->stream>>>(
+                    d_text, n, ctx->lut, s_bits, K, ctx->keys[0], ctx->ids[0], ctx->hist, passes0);
+        }
+#undef INIT_PACKED
         LAUNCHED();
     }
     span_end(ctx, sp);
@@ -337,6 +372,12 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     cur ^= 1;  // the compacted active ids now live in ids[cur]
     u32 m = 0;
     if (int rc = fetch_count(ctx, &m)) return rc;
+    if (m > 0) {  // ranks are needed only if another round follows
+        sp = span_begin(ctx, PH_RERANK);
+        k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, m, ctx->isa);
+        LAUNCHED();
+        span_end(ctx, sp);
+    }
 
     // ---- doubling rounds
     u64 h = (u64)K;
@@ -489,12 +530,6 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
         ctx->events[i] = nullptr;
         if (cudaEventCreate(&ctx->events[i]) != cudaSuccess) return bail(DARK_BWT_E_CUDA);
     }
-    typedef OnesweepSmem<kSortThreads, kSortItems> Smem;
-    if (cudaFuncSetAttribute(k_onesweep_pass<kSortThreads, kSortItems, u32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(Smem)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_onesweep_pass<kSortThreads, kSortItems, u64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(Smem)) != cudaSuccess)
-        return bail(DARK_BWT_E_CUDA);
     if (cudaMemsetAsync(ctx->scalars, 0, sizeof(DeviceScalars), ctx->stream) != cudaSuccess) return bail(DARK_BWT_E_CUDA);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return bail(DARK_BWT_E_CUDA);
     *out = ctx;

@@ -101,8 +101,8 @@ struct OnesweepSmem {
     u32 tile;
 };
 
-template <int THREADS, int ITEMS, typename StatusT>
-__global__ void __launch_bounds__(THREADS)
+template <int THREADS, int ITEMS, int MINBLOCKS, typename StatusT>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS)
 k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
                 u32* __restrict__ vals_out, u32 m, int shift, const u32* __restrict__ digit_base,
                 StatusT* __restrict__ status, u32* __restrict__ tile_counter) {
@@ -128,27 +128,34 @@ k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in
     // so every load instruction of a warp covers 32 consecutive pairs and rank order == index order.
     const u32 local0 = warp * (32 * ITEMS) + lane;
     u64 key[ITEMS];
-    u32 val[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const u32 li = local0 + k * 32;
         key[k] = (li < nvalid) ? ld_stream(keys_in + tile_base + li) : ~0ull;
     }
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const u32 li = local0 + k * 32;
-        val[k] = (li < nvalid) ? ld_stream(vals_in + tile_base + li) : 0u;
-    }
 
-    // ---- rank inside the warp: match_any groups equal digits, the lowest lane bumps the counter
-    u32 rank[ITEMS];
+    // ---- rank inside the warp: lanes with equal digits are found with 8 ballots (one per digit
+    // bit; the match.any instruction is microcoded per distinct value and was the top stall of the
+    // first version, profiles/r1_ncu_c2_v1.md); the lowest lane of each group bumps the counter.
+    static_assert(ITEMS % 2 == 0, "ranks are packed two per register");
+    u32 rank2[ITEMS / 2];  // 16-bit ranks (< 32*ITEMS), two per register
     u32* whist = s.warp_hist[warp];
     const u32 lt = lanemask_lt();
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const bool valid = (local0 + k * 32) < nvalid;
-        const u32 d = valid ? digit_of(key[k], shift) : (u32)kRadix;  // invalid lanes group apart
-        const u32 peers = __match_any_sync(0xffffffffu, d);
+        u32 d = digit_of(key[k], shift);
+        // Tie this item's ballots to the result of item k-2: without the false dependency the
+        // compiler hoists the votes of all ITEMS items to the top (150+ registers, one CTA per SM).
+        if (k >= 2) asm volatile("" : "+r"(d) : "r"(rank2[(k - 2) / 2]));
+        u32 peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int b = 0; b < kRadixBits; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const u32 vote = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? vote : ~vote;
+        }
+        if (!valid) peers = 1u << lane;  // padding lanes stand alone and count nothing
         const int leader = __ffs(peers) - 1;
         u32 prev = 0;
         if (lane == leader && valid) {
@@ -156,10 +163,21 @@ k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in
             whist[d] = prev + __popc(peers);
         }
         prev = __shfl_sync(0xffffffffu, prev, leader);
-        rank[k] = prev + __popc(peers & lt);
+        const u32 r = prev + __popc(peers & lt);
+        if (k & 1) rank2[k / 2] |= r << 16;
+        else rank2[k / 2] = r;
         __syncwarp();
     }
     __syncthreads();
+
+    // values are fetched only now, so they do not occupy registers during the ranking loop; their
+    // latency overlaps the digit scan below
+    u32 val[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u32 li = local0 + k * 32;
+        val[k] = (li < nvalid) ? ld_stream(vals_in + tile_base + li) : 0u;
+    }
 
     // ---- per-digit: exclusive offsets across warps, tile total, publish, look back
     u32 count = 0;
@@ -184,12 +202,29 @@ k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in
     }
     if (tid < kRadix && lane == 31) s.warp_sum[warp] = incl;
     __syncthreads();
+    u32 dstart = 0;
     if (tid < kRadix) {
         u32 wbase = 0;
         for (int w = 0; w < warp; ++w) wbase += s.warp_sum[w];
-        const u32 dstart = wbase + incl - count;
+        dstart = wbase + incl - count;
         s.digit_start[tid] = dstart;
+    }
+    __syncthreads();
 
+    // ---- re-order the tile by digit in shared memory (needs only tile-local offsets, so it runs
+    // before the look-back and gives the predecessor tiles time to publish)
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if ((local0 + k * 32) < nvalid) {
+            const u32 d = digit_of(key[k], shift);
+            const u32 pos = s.digit_start[d] + whist[d] + ((rank2[k / 2] >> (16 * (k & 1))) & 0xFFFFu);
+            s.keys[pos] = key[k];
+            s.vals[pos] = val[k];
+        }
+    }
+
+    // ---- decoupled look-back over the predecessors' digit counts
+    if (tid < kRadix) {
         StatusT excl = 0;
         if (tile > 0) {
             int t = (int)tile - 1;
@@ -204,18 +239,6 @@ k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in
             st_relaxed(status + (size_t)tile * kRadix + tid, ((StatusT)2 << ST::kShift) | (excl + count));
         }
         s.global_off[tid] = digit_base[tid] + (u32)excl - dstart;
-    }
-    __syncthreads();
-
-    // ---- re-order the tile by digit in shared memory
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        if ((local0 + k * 32) < nvalid) {
-            const u32 d = digit_of(key[k], shift);
-            const u32 pos = s.digit_start[d] + whist[d] + rank[k];
-            s.keys[pos] = key[k];
-            s.vals[pos] = val[k];
-        }
     }
     __syncthreads();
 

@@ -110,6 +110,61 @@ k_init_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ lut, int 
     hist_flush(s_hist, g_hist, num_passes, tid, THREADS);
 }
 
+// Fast path for s in {1,2,4,8} bits per symbol (sigma <= 2, 4, 16, 256): the tile's codes are first
+// packed MSB-first into 32-bit words in shared memory; a key is then a 64-bit window of that bit
+// stream (3 LDS + 2 funnel shifts instead of K byte loads — the byte loop made the first version
+// of this kernel issue-bound at K = 32, profiles/r1_ncu_c2_v1.md).
+template <int THREADS, int ITEMS, int S>
+__global__ void __launch_bounds__(THREADS)
+k_init_keys_packed(const u8* __restrict__ text, u32 n, const u8* __restrict__ lut, u64* __restrict__ keys_out,
+                   u32* __restrict__ ids_out, u32* __restrict__ g_hist) {
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int SPW = 32 / S;   // symbols per word
+    constexpr int K = 64 / S;     // symbols per key: exactly two words
+    constexpr int NWORDS = (TILE + K) / SPW + 3;
+    __shared__ u32 s_words[NWORDS];
+    __shared__ u8 s_lut[256];
+    __shared__ u32 s_hist[kMaxPasses * kRadix];
+    const int tid = threadIdx.x;
+    hist_clear(s_hist, tid, THREADS);
+    for (int i = tid; i < 256; i += THREADS) s_lut[i] = lut[i];
+    __syncthreads();
+
+    const u64 jb = (u64)blockIdx.x * TILE;
+    const u32 cnt = (u32)min((u64)TILE, (u64)n - jb);
+    const u64 i_lo = (u64)n - jb - cnt;
+    for (int w = tid; w < NWORDS; w += THREADS) {
+        u32 word = 0;
+        const u64 pos0 = i_lo + (u64)w * SPW;
+#pragma unroll
+        for (int c = 0; c < SPW; ++c) {
+            const u64 pos = pos0 + c;
+            const u32 code = pos < n ? (u32)s_lut[text[pos]] : 0u;
+            word = (S == 32 ? 0u : (word << (S & 31))) | code;
+        }
+        s_words[w] = word;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < ITEMS; ++k) {
+        const u32 jl = k * THREADS + tid;
+        if (jl < cnt) {
+            const u32 x = cnt - 1 - jl;
+            const u32 bit = x * S;
+            const u32 wi = bit >> 5, sh = bit & 31;
+            const u32 w0 = s_words[wi], w1 = s_words[wi + 1], w2 = s_words[wi + 2];
+            const u32 hi = __funnelshift_l(w1, w0, sh);
+            const u32 lo = __funnelshift_l(w2, w1, sh);
+            const u64 key = ((u64)hi << 32) | lo;
+            keys_out[jb + jl] = key;
+            ids_out[jb + jl] = (u32)(i_lo + x);
+            hist_add_key(s_hist, key, 0, kMaxPasses);
+        }
+    }
+    __syncthreads();
+    hist_flush(s_hist, g_hist, kMaxPasses, tid, THREADS);
+}
+
 // ---- round r >= 1: keys (rank[i], rank[i+h]) ------------------------------------------------------
 // Active element p: suffix ids[p] in a group of rank ranks[p].  key = rank << kb | (isa[i+h]+1 or 0).
 // Fused: digit histogram.  HBM: 8 B read + one 4-byte gather (a 32 B sector) + 8 B written per element.
@@ -364,9 +419,13 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
             const u32 r_new = r_old + (run.hs1 - run.gs1);
             const u32 sid = id[k + 1];
             const bool single = ((newh >> k) & 1) && ((newh >> (k + 1)) & 1);
-            if (ROUND0 || r_new != r_old) isa[sid] = r_new;
+            // Round 0 leaves isa[] alone: if nothing survives (DNA-like blocks) the ranks are never
+            // read, otherwise k_round0_isa scatters them afterwards.  It writes every SA slot
+            // (SUF_INVALID for unsettled ones) so that kernel can tell which slots are final.
+            if (!ROUND0 && r_new != r_old) isa[sid] = r_new;
+            if (ROUND0) sa[p] = single ? sid : 0xFFFFFFFFu;
             if (single) {
-                sa[r_new] = sid;
+                if (!ROUND0) sa[r_new] = sid;
             } else {
                 out_ids[run.cnt] = sid;
                 out_ranks[run.cnt] = r_new;
@@ -374,6 +433,20 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
             }
         }
     }
+}
+
+// Deferred rank scatter of round 0 (only launched when suffixes survive round 0):
+// settled slots give isa[SA[p]] = p, survivors give isa[id] = rank of their group.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_round0_isa(const u32* __restrict__ sa, u32 n, const u32* __restrict__ act_ids, const u32* __restrict__ act_ranks, u32 m,
+             u32* __restrict__ isa) {
+    const u64 p = (u64)blockIdx.x * THREADS + threadIdx.x;
+    if (p < n) {
+        const u32 v = ld_stream(sa + p);
+        if (v != 0xFFFFFFFFu) isa[v] = (u32)p;
+    }
+    if (p < m) isa[ld_stream(act_ids + p)] = ld_stream(act_ranks + p);
 }
 
 // ---- BWT emission ---------------------------------------------------------------------------------
