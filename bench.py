@@ -37,7 +37,7 @@ WORKLOADS = {
     "c1": ("text", 3, 768771, "C1: 768 KB English-like text block text(seed=3)", 366.437),
     "c2": ("dna", 1, 1 << 28, "C2: 256 MiB synthetic DNA-like 4-symbol block dna(seed=1+rank)", 497.5),
     "c3": ("rep17", 2, 1 << 26, "C3: 64 MiB period-17 block with sparse mutations rep17(seed=2+rank)", 2342.0),
-    "c4": ("mixed", 4, 1 << 31, "C4: 2 GiB mixed binary/text block mixed(seed=4+rank)", 445.0),
+    "c4": ("mixed", 4, 1 << 31, "C4: 2 GiB mixed binary/text block mixed(seed=4+rank)", 461.4),
     "c5": ("mixed", 1000, 1 << 28, "C5 block: 256 MiB mixed binary/text block mixed(seed=1000+rank)", 445.8),
 }
 

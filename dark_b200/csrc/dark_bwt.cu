@@ -27,8 +27,6 @@ using namespace dark;
 
 namespace {
 
-constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;
 constexpr int kSortTile = 3072;  // smallest tile of any pass variant (sizes the status buffer)
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
@@ -92,9 +90,7 @@ struct dark_bwt_ctx {
     void* sort_status = nullptr;
     size_t sort_status_bytes = 0;
     u32* counters = nullptr;
-    u32* scan_flag = nullptr;
-    uint4* scan_agg = nullptr;
-    uint4* scan_incl = nullptr;
+    u64* scan_words = nullptr;
     size_t scan_tiles = 0;
 
     Mailbox* mail = nullptr;
@@ -185,7 +181,7 @@ int launch_pass_variant(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* 
     return 0;
 }
 
-constexpr int kDefaultSortVariant = 0;
+constexpr int kDefaultSortVariant = 5;  // 512 threads x 12 items, 2 CTAs/SM: best of the sweep in profiles/r1_sort_variants_v2.log
 
 // One onesweep pass over m pairs: buffers[cur] -> buffers[cur^1].
 int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
@@ -206,6 +202,10 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
         case 5: V(512, 12, 2);
         case 6: V(256, 12, 3);
         case 7: V(1024, 4, 1);
+        case 8: V(256, 8, 4);
+        case 9: V(256, 8, 5);
+        case 10: V(512, 10, 2);
+        case 11: V(512, 14, 2);
         default: V(256, 16, 2);
     }
 #undef V
@@ -245,8 +245,8 @@ int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32
     if (tiles > ctx->scan_tiles) return ctx->fail_internal("scan tile state too small");
     u32* counter = nullptr;
     if (int rc = next_counter(ctx, &counter)) return rc;
-    CK(cudaMemsetAsync(ctx->scan_flag, 0, sizeof(u32) * tiles, ctx->stream));
-    ScanTileState ts{ctx->scan_flag, ctx->scan_agg, ctx->scan_incl};
+    CK(cudaMemsetAsync(ctx->scan_words, 0, sizeof(u64) * kScanWordsPerTile * tiles, ctx->stream));
+    ScanTileState ts{ctx->scan_words};
     k_rerank<kScanThreads, kScanItems, ROUND0><<<tiles, kScanThreads, 0, ctx->stream>>>(
         keys, ids, m, n, K, kb, ctx->isa, sa, out_ids, ctx->ranks, ts, counter, &ctx->scalars->count);
     LAUNCHED();
@@ -489,9 +489,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     const size_t o_scalars = carve(sizeof(DeviceScalars));
     const size_t o_status = carve(ctx->sort_status_bytes);
     const size_t o_counters = carve(sizeof(u32) * kMaxCounters);
-    const size_t o_sflag = carve(sizeof(u32) * ctx->scan_tiles);
-    const size_t o_sagg = carve(sizeof(uint4) * ctx->scan_tiles);
-    const size_t o_sincl = carve(sizeof(uint4) * ctx->scan_tiles);
+    const size_t o_swords = carve(sizeof(u64) * kScanWordsPerTile * ctx->scan_tiles);
     ctx->arena_bytes = off;
 
     auto bail = [&](int code) {
@@ -519,9 +517,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     ctx->scalars = (DeviceScalars*)(base + o_scalars);
     ctx->sort_status = base + o_status;
     ctx->counters = (u32*)(base + o_counters);
-    ctx->scan_flag = (u32*)(base + o_sflag);
-    ctx->scan_agg = (uint4*)(base + o_sagg);
-    ctx->scan_incl = (uint4*)(base + o_sincl);
+    ctx->scan_words = (u64*)(base + o_swords);
 
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DARK_BWT_E_CUDA);
     if (cudaHostAlloc((void**)&ctx->mail, sizeof(Mailbox), cudaHostAllocDefault) != cudaSuccess) return bail(DARK_BWT_E_NOMEM);

@@ -226,32 +226,17 @@ __device__ __forceinline__ ScanTriple shfl_up_triple(ScanTriple v, int o) {
     r.cnt = __shfl_up_sync(0xffffffffu, v.cnt, o);
     return r;
 }
-__device__ __forceinline__ ScanTriple shfl_xor_triple(ScanTriple v, int o) {
-    ScanTriple r;
-    r.gs1 = __shfl_xor_sync(0xffffffffu, v.gs1, o);
-    r.hs1 = __shfl_xor_sync(0xffffffffu, v.hs1, o);
-    r.cnt = __shfl_xor_sync(0xffffffffu, v.cnt, o);
-    return r;
-}
-__device__ __forceinline__ void st_payload(uint4* p, ScanTriple v) {
-    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.gs1), "r"(v.hs1), "r"(v.cnt), "r"(0u)
-                 : "memory");
-}
-__device__ __forceinline__ ScanTriple ld_payload(const uint4* p) {
-    ScanTriple v;
-    u32 pad;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.gs1), "=r"(v.hs1), "=r"(v.cnt), "=r"(pad) : "l"(p) : "memory");
-    return v;
-}
-
-// Scan tile descriptors: flag[t] (0 = empty, 1 = aggregate ready, 2 = inclusive ready) with the
-// payloads in separate write-once arrays; payload store -> fence -> flag store on the producer,
-// flag load -> fence -> payload load on the consumer.
+// Scan tile descriptors: three self-describing 64-bit words per tile, one per scanned quantity:
+// [flag:2 | value:32], flag 0 = empty, 1 = tile aggregate, 2 = inclusive prefix.  Value and flag
+// travel in one word, so relaxed gpu-scope accesses suffice and no fence sits on the look-back
+// path (the first version published a 16-byte payload behind a flag with three __threadfence()
+// per tile and ran at 1.2 TB/s, profiles/r1_ncu_c5_c3_v2.md).  The three words of a tile may be
+// observed in different states; each quantity is therefore resolved independently.
 struct ScanTileState {
-    u32* flag;
-    uint4* agg;
-    uint4* incl;
+    u64* words;  // [tiles][4]  (gs1, hs1, cnt, pad)
 };
+constexpr int kScanWordsPerTile = 4;
+__device__ __forceinline__ u64 scan_pack(u32 flag, u32 value) { return ((u64)flag << 62) | value; }
 
 template <int THREADS, int ITEMS, bool ROUND0>
 __global__ void __launch_bounds__(THREADS)
@@ -356,49 +341,53 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
     if (lane == 0) texcl = ScanTriple{0u, 0u, 0u};
     texcl = scan_combine(wprefix, texcl);  // exclusive prefix of this thread inside the tile
 
-    // tile aggregate -> publish, look back (warp 0)
+    // tile aggregate -> publish, look back over a 32-tile window per step (warp 0)
     if (warp == 0) {
         ScanTriple tile_agg = {0u, 0u, 0u};
         for (int w = 0; w < WARPS; ++w) tile_agg = scan_combine(tile_agg, s_warp[w]);
         ScanTriple excl = {0u, 0u, 0u};
+        u64* mine = ts.words + (size_t)tile * kScanWordsPerTile;
         if (tile == 0) {
-            if (lane == 0) {
-                st_payload(ts.incl + 0, tile_agg);
-                __threadfence();
-                st_relaxed(ts.flag + 0, 2u);
-            }
+            if (lane < 3) st_relaxed(mine + lane, scan_pack(2u, lane == 0 ? tile_agg.gs1 : lane == 1 ? tile_agg.hs1 : tile_agg.cnt));
         } else {
-            if (lane == 0) {
-                st_payload(ts.agg + tile, tile_agg);
-                __threadfence();
-                st_relaxed(ts.flag + tile, 1u);
-            }
+            if (lane < 3) st_relaxed(mine + lane, scan_pack(1u, lane == 0 ? tile_agg.gs1 : lane == 1 ? tile_agg.hs1 : tile_agg.cnt));
             int base = (int)tile - 1;
-            for (;;) {
+            u32 pending = 7u;  // bit c set: quantity c has not met an inclusive prefix yet
+            while (pending) {
                 const int t = base - lane;
-                u32 f = 2;
+                u64 w0 = scan_pack(2u, 0u), w1 = w0, w2 = w0;  // virtual tiles before tile 0: inclusive identity
                 if (t >= 0) {
-                    do {
-                        f = ld_relaxed(ts.flag + t);
-                    } while (f == 0);
+                    const u64* theirs = ts.words + (size_t)t * kScanWordsPerTile;
+                    do { w0 = ld_relaxed(theirs + 0); } while ((w0 >> 62) == 0);
+                    do { w1 = ld_relaxed(theirs + 1); } while ((w1 >> 62) == 0);
+                    do { w2 = ld_relaxed(theirs + 2); } while ((w2 >> 62) == 0);
                 }
-                __threadfence();
-                ScanTriple v = {0u, 0u, 0u};
-                if (t >= 0) v = ld_payload((f == 2 ? ts.incl : ts.agg) + t);
-                const u32 im = __ballot_sync(0xffffffffu, f == 2);
-                const int first = im ? (__ffs(im) - 1) : 32;  // nearest tile with an inclusive prefix
-                if (lane > first) v = ScanTriple{0u, 0u, 0u};
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v = scan_combine(v, shfl_xor_triple(v, o));  // ops commute
-                excl = scan_combine(v, excl);
-                if (im) break;
+                // quantity 0: latest old-group head (max)
+                if (pending & 1u) {
+                    const u32 im = __ballot_sync(0xffffffffu, (w0 >> 62) == 2);
+                    const int first = im ? (__ffs(im) - 1) : 31;
+                    const u32 v = __reduce_max_sync(0xffffffffu, lane <= first ? (u32)w0 : 0u);
+                    excl.gs1 = max(excl.gs1, v);
+                    if (im) pending &= ~1u;
+                }
+                if (pending & 2u) {
+                    const u32 im = __ballot_sync(0xffffffffu, (w1 >> 62) == 2);
+                    const int first = im ? (__ffs(im) - 1) : 31;
+                    const u32 v = __reduce_max_sync(0xffffffffu, lane <= first ? (u32)w1 : 0u);
+                    excl.hs1 = max(excl.hs1, v);
+                    if (im) pending &= ~2u;
+                }
+                if (pending & 4u) {
+                    const u32 im = __ballot_sync(0xffffffffu, (w2 >> 62) == 2);
+                    const int first = im ? (__ffs(im) - 1) : 31;
+                    const u32 v = __reduce_add_sync(0xffffffffu, lane <= first ? (u32)w2 : 0u);
+                    excl.cnt += v;
+                    if (im) pending &= ~4u;
+                }
                 base -= 32;
             }
-            if (lane == 0) {
-                st_payload(ts.incl + tile, scan_combine(excl, tile_agg));
-                __threadfence();
-                st_relaxed(ts.flag + tile, 2u);
-            }
+            const ScanTriple inc = scan_combine(excl, tile_agg);
+            if (lane < 3) st_relaxed(mine + lane, scan_pack(2u, lane == 0 ? inc.gs1 : lane == 1 ? inc.hs1 : inc.cnt));
         }
         if (lane == 0) {
             s_excl = excl;

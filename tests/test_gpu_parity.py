@@ -239,7 +239,8 @@ def test_gpu_verifier_accepts_and_rejects(saca, oracle, torch):
 
 
 # ---- large: fixtures + the independent GPU verifier ---------------------------
-LARGE = ["dna:1:16777216", "mixed:4:16777216", "rep17:2:67108864", "dna:1:268435456", "mixed:1000:268435456"]
+LARGE = ["dna:1:16777216", "mixed:4:16777216", "rep17:2:67108864", "dna:1:268435456", "mixed:1000:268435456",
+         "mixed:4:2147483648"]   # the last one is C4: 2 GiB block, 64-bit offsets, 64-bit tile status
 
 
 @pytest.mark.parametrize("key", LARGE)
