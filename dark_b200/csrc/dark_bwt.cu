@@ -44,6 +44,7 @@ struct Mailbox {  // pinned host memory the device results are copied into
     u32 sigma;
     u32 count;
     u32 trivial[kMaxPasses];
+    float collide[kMaxPasses];
     u64 origin;
     unsigned long long bad;
 };
@@ -52,6 +53,7 @@ struct DeviceScalars {  // mirrors Mailbox on the device
     u32 sigma;
     u32 count;
     u32 trivial[kMaxPasses];
+    float collide[kMaxPasses];
     u64 origin;
     unsigned long long bad;
 };
@@ -91,6 +93,7 @@ struct dark_bwt_ctx {
     size_t sort_status_bytes = 0;
     u32* counters = nullptr;
     u64* scan_words = nullptr;
+    u32* bitmap = nullptr;  // n bits: positions whose rank the next round reads
     size_t scan_tiles = 0;
 
     Mailbox* mail = nullptr;
@@ -213,15 +216,42 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
 
 // Sort passes for a histogram that is already in ctx->hist (counts).  `cur` is the index of the
 // (keys, ids) pair holding the input; returns the index holding the output through *cur_out.
+//
+// Pass pruning (round 0 only, `prune`): an LSD sort of the top t digits alone orders the keys by
+// their leading 8t bits; whatever stays tied is finished by the doubling rounds.  With S_p the
+// probability that two keys share digit p (from the histogram), about m * prod(S_p) of the keys
+// keep a partner after the top t digits, IF the digits are independent.  That holds for
+// high-entropy blocks (packed DNA, random bytes) and fails badly for text, where a shallower
+// initial sort also slows every later round (h starts smaller).  So the low digits are dropped
+// only when every digit is close to uniform (S_p <= 1.5/256) and the estimate leaves < 1/64 of the
+// block tied; measured: C2 8 -> 5 passes + one 65,792-element round; C1/C5 unchanged.
+// *first_pass_out = index of the lowest digit that was sorted.
 int run_sort(dark_bwt_ctx* ctx, u64* const keys[2], u32* const vals[2], int cur, u32 m, int begin_bit, int num_passes,
-             int* cur_out, dark_bwt_stats* st, int round) {
-    k_scan_hist<<<num_passes, kRadix, 0, ctx->stream>>>(ctx->hist, m, ctx->scalars->trivial);
+             int* cur_out, dark_bwt_stats* st, int round, bool prune = false, int* first_pass_out = nullptr) {
+    k_scan_hist<<<num_passes, kRadix, 0, ctx->stream>>>(ctx->hist, m, ctx->scalars->trivial, ctx->scalars->collide);
     LAUNCHED();
-    CK(cudaMemcpyAsync(ctx->mail->trivial, ctx->scalars->trivial, sizeof(u32) * kMaxPasses, cudaMemcpyDeviceToHost,
-                       ctx->stream));
+    CK(cudaMemcpyAsync(ctx->mail->trivial, ctx->scalars->trivial, (sizeof(u32) + sizeof(float)) * kMaxPasses,
+                       cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    int first = 0;
+    if (prune) {
+        for (int p = 0; p < num_passes; ++p)
+            if (ctx->mail->collide[p] > 1.5f / 256.0f) prune = false;  // not a high-entropy block
+    }
+    if (prune) {
+        double tied = (double)m;  // m * P(two keys agree on the top t digits) ~ fraction of keys left with a partner
+        int t = 0;
+        for (int p = num_passes - 1; p >= 0; --p) {
+            tied *= (double)ctx->mail->collide[p];
+            ++t;
+            if (tied * 64.0 <= 1.0) break;
+        }
+        first = num_passes - t;
+        if (first < 0) first = 0;
+    }
+    if (first_pass_out) *first_pass_out = first;
     const int sp = span_begin(ctx, PH_PASS);
-    for (int p = 0; p < num_passes; ++p) {
+    for (int p = first; p < num_passes; ++p) {
         if (ctx->mail->trivial[p]) continue;  // every key has the same digit: the pass is the identity
         if (int rc = launch_pass(ctx, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], m, begin_bit + p * kRadixBits,
                                  ctx->hist + p * kRadix))
@@ -330,7 +360,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     if (sigma < 1 || sigma > 256) return ctx->fail_internal("alphabet scan returned an impossible sigma");
     const int s_bits = no_pack ? 8 : std::max(1, bit_length(sigma - 1));
     const int K = 64 / s_bits;
-    const int passes0 = (s_bits * K + kRadixBits - 1) / kRadixBits;
+    const int passes0 = kMaxPasses;  // the symbol field is MSB-aligned in the 64-bit key
     if (st) {
         st->sigma = sigma;
         st->bits_per_symbol = s_bits;
@@ -358,29 +388,48 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     span_end(ctx, sp);
 
     int cur = 0;
+    int first_pass = 0;
     sp = span_begin(ctx, PH_SORT);
-    if (int rc = run_sort(ctx, ctx->keys, ctx->ids, cur, n, 0, passes0, &cur, st, 0)) return rc;
+    if (int rc = run_sort(ctx, ctx->keys, ctx->ids, cur, n, 0, passes0, &cur, st, 0, /*prune=*/!no_pack, &first_pass)) return rc;
     span_end(ctx, sp);
+    // The sort covered the key bits above `drop`: K0 whole leading symbols are known equal inside a
+    // tie group, Kc symbols were touched (a suffix shorter than Kc had padding compared).
+    const int drop = first_pass * kRadixBits;
+    const int sorted_bits = 64 - drop;
+    const int K0 = std::min(K, sorted_bits / s_bits);
+    const int Kc = std::min(K, (sorted_bits + s_bits - 1) / s_bits);
+    if (K0 < 1) return ctx->fail_internal("initial sort covered less than one symbol");
+    if (st) st->initial_symbols = K0;
 
     const int kb = bit_length(n);  // rank2 = isa+1 in [0, n]
     const int key_bits = kb + bit_length((u64)n - 1);
     const int passes_r = (key_bits + kRadixBits - 1) / kRadixBits;
 
     sp = span_begin(ctx, PH_RERANK);
-    if (int rc = launch_rerank<true>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, K, kb, sa, ctx->ids[cur ^ 1])) return rc;
+    if (int rc = launch_rerank<true>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, Kc, drop, sa, ctx->ids[cur ^ 1])) return rc;
     span_end(ctx, sp);
     cur ^= 1;  // the compacted active ids now live in ids[cur]
     u32 m = 0;
     if (int rc = fetch_count(ctx, &m)) return rc;
-    if (m > 0) {  // ranks are needed only if another round follows
+
+    // Round 0 wrote no ranks.  If a round follows they are needed: all of them when many suffixes
+    // survive; otherwise only the survivors' now, and per round the few that are actually read.
+    bool isa_complete = true;
+    int selective_rounds = 0;
+    if (m > 0) {
         sp = span_begin(ctx, PH_RERANK);
-        k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, m, ctx->isa);
+        if (m > n / 16) {
+            k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, m, ctx->isa);
+        } else {
+            k_scatter_ranks<256><<<(u32)ceil_div(m, 256), 256, 0, ctx->stream>>>(ctx->ids[cur], ctx->ranks, m, ctx->isa);
+            isa_complete = false;
+        }
         LAUNCHED();
         span_end(ctx, sp);
     }
 
     // ---- doubling rounds
-    u64 h = (u64)K;
+    u64 h = (u64)K0;
     int round = 1;
     while (m > 0) {
         if (round >= DARK_BWT_MAX_ROUNDS || h >= 2 * (u64)n + 2) return ctx->fail_internal("prefix doubling did not converge");
@@ -389,6 +438,22 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
             st->rounds = round;
         }
         sp = span_begin(ctx, PH_KEYBUILD);
+        if (!isa_complete) {
+            // ranks of suffixes settled in round 0 exist only where they are about to be read
+            if (selective_rounds < 2) {
+                const size_t words = (size_t)ceil_div(n, 32);
+                CK(cudaMemsetAsync(ctx->bitmap, 0, words * sizeof(u32), ctx->stream));
+                k_mark_needed<256><<<(u32)ceil_div(m, 256), 256, 0, ctx->stream>>>(ctx->ids[cur], m, n, h, ctx->bitmap);
+                LAUNCHED();
+                k_fill_needed<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->bitmap, ctx->isa);
+                LAUNCHED();
+                ++selective_rounds;
+            } else {  // still not done after two rounds: fill every settled rank once
+                k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, 0u, ctx->isa);
+                LAUNCHED();
+                isa_complete = true;
+            }
+        }
         CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
         {
             const u32 blocks = (u32)ceil_div(m, kBuildThreads * kBuildItems);
@@ -489,6 +554,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     const size_t o_scalars = carve(sizeof(DeviceScalars));
     const size_t o_status = carve(ctx->sort_status_bytes);
     const size_t o_counters = carve(sizeof(u32) * kMaxCounters);
+    const size_t o_bitmap = carve(sizeof(u32) * (ceil_div(N, 32) + 1));
     const size_t o_swords = carve(sizeof(u64) * kScanWordsPerTile * ctx->scan_tiles);
     ctx->arena_bytes = off;
 
@@ -518,6 +584,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     ctx->sort_status = base + o_status;
     ctx->counters = (u32*)(base + o_counters);
     ctx->scan_words = (u64*)(base + o_swords);
+    ctx->bitmap = (u32*)(base + o_bitmap);
 
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DARK_BWT_E_CUDA);
     if (cudaHostAlloc((void**)&ctx->mail, sizeof(Mailbox), cudaHostAllocDefault) != cudaSuccess) return bail(DARK_BWT_E_NOMEM);

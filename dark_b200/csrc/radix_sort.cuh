@@ -50,8 +50,12 @@ __global__ void __launch_bounds__(THREADS) k_digit_hist(const u64* __restrict__ 
 
 // Counts -> exclusive digit bases, in place; one CTA of kRadix threads per pass.
 // trivial[p] = 1 when a single digit holds all m keys (the pass would be the identity).
-__global__ void __launch_bounds__(kRadix) k_scan_hist(u32* __restrict__ g_hist, u32 m, u32* __restrict__ trivial) {
+// collide[p] = sum_d (c_d / m)^2: the probability that two random keys share digit p — used by the
+// host to decide how many of the low digits of the initial sort can be skipped (pass pruning).
+__global__ void __launch_bounds__(kRadix) k_scan_hist(u32* __restrict__ g_hist, u32 m, u32* __restrict__ trivial,
+                                                      float* __restrict__ collide) {
     __shared__ u32 s_warp[kRadix / 32];
+    __shared__ float s_sq[kRadix / 32];
     __shared__ u32 s_triv;
     const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
     u32* row = g_hist + blockIdx.x * kRadix;
@@ -60,17 +64,27 @@ __global__ void __launch_bounds__(kRadix) k_scan_hist(u32* __restrict__ g_hist, 
     const u32 c = row[d];
     if (c == m) s_triv = 1;
     u32 incl = c;
+    const float f = (float)c / (float)m;
+    float sq = f * f;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         u32 t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_sq[warp] = sq;
     __syncthreads();
     u32 base = 0;
     for (int w = 0; w < warp; ++w) base += s_warp[w];
     row[d] = base + incl - c;
-    if (d == 0) trivial[blockIdx.x] = s_triv;
+    if (d == 0) {
+        trivial[blockIdx.x] = s_triv;
+        float tot = 0.f;
+        for (int w = 0; w < kRadix / 32; ++w) tot += s_sq[w];
+        collide[blockIdx.x] = tot;
+    }
 }
 
 // ---- the onesweep pass ------------------------------------------------------------------------

@@ -101,6 +101,7 @@ k_init_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ lut, int 
             const u32 x = cnt - 1 - jl;  // position i = i_lo + x
             u64 key = 0;
             for (int c = 0; c < K; ++c) key = (key << s_bits) | s_code[x + c];
+            key <<= (64 - s_bits * K);  // symbol field MSB-aligned, so "the top 8t bits" are whole leading symbols
             keys_out[jb + jl] = key;
             ids_out[jb + jl] = (u32)(i_lo + x);
             hist_add_key(s_hist, key, 0, num_passes);
@@ -302,11 +303,12 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
             nh = true;
             oh = true;
         } else {
-            nh = key[k + 1] != key[k];
             if (ROUND0) {
-                nh = nh || id[k + 1] >= short_from || id[k] >= short_from;
+                // round 0 sorted only the bits above kb (pass pruning): ties on those bits are groups
+                nh = (key[k + 1] >> kb) != (key[k] >> kb) || id[k + 1] >= short_from || id[k] >= short_from;
                 oh = false;
             } else {
+                nh = key[k + 1] != key[k];
                 oh = (key[k + 1] >> kb) != (key[k] >> kb);
             }
         }
@@ -436,6 +438,35 @@ k_round0_isa(const u32* __restrict__ sa, u32 n, const u32* __restrict__ act_ids,
         if (v != 0xFFFFFFFFu) isa[v] = (u32)p;
     }
     if (p < m) isa[ld_stream(act_ids + p)] = ld_stream(act_ranks + p);
+}
+
+// Rank scatter of the survivors alone: isa[id] = rank of its group (m elements).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_scatter_ranks(const u32* __restrict__ act_ids, const u32* __restrict__ act_ranks, u32 m, u32* __restrict__ isa) {
+    const u64 p = (u64)blockIdx.x * THREADS + threadIdx.x;
+    if (p < m) isa[ld_stream(act_ids + p)] = ld_stream(act_ranks + p);
+}
+
+// Selective rank fill (few survivors after round 0): the next round reads isa[i+h] for the
+// active i only, so mark those positions in an n-bit map (L2-resident: n/8 bytes) ...
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_mark_needed(const u32* __restrict__ act_ids, u32 m, u32 n, u64 h, u32* __restrict__ bitmap) {
+    const u64 p = (u64)blockIdx.x * THREADS + threadIdx.x;
+    if (p >= m) return;
+    const u64 j = (u64)ld_stream(act_ids + p) + h;
+    if (j < n) atomicOr(bitmap + (j >> 5), 1u << (j & 31));
+}
+// ... then stream over the suffix array once and write the rank (= slot) of the marked suffixes
+// that are already settled.  Unsettled ones had their rank scattered as survivors.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_fill_needed(const u32* __restrict__ sa, u32 n, const u32* __restrict__ bitmap, u32* __restrict__ isa) {
+    const u64 p = (u64)blockIdx.x * THREADS + threadIdx.x;
+    if (p >= n) return;
+    const u32 v = ld_stream(sa + p);
+    if (v != 0xFFFFFFFFu && ((__ldg(bitmap + (v >> 5)) >> (v & 31)) & 1u)) isa[v] = (u32)p;
 }
 
 // ---- BWT emission ---------------------------------------------------------------------------------

@@ -15,6 +15,8 @@ pub struct dark_bwt_stats {
     pub sigma: u32,
     pub bits_per_symbol: u32,
     pub symbols_per_key: u32,
+    pub initial_symbols: u32,
+    pub reserved0: u32,
     pub rounds: u32,
     pub sort_passes: u32,
     pub kernel_launches: u32,
