@@ -56,6 +56,7 @@ struct DeviceScalars {  // mirrors Mailbox on the device
     float collide[kMaxPasses];
     u64 origin;
     unsigned long long bad;
+    u32 pair_total;  // device only: number of valid pairs of the current bucketed scatter
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -93,6 +94,7 @@ struct dark_bwt_ctx {
     size_t sort_status_bytes = 0;
     u32* counters = nullptr;
     u64* scan_words = nullptr;
+    u32* bucket_hist = nullptr;  // 256 counters / cursors of the bucketed rank scatter
     u32* bitmap = nullptr;  // n bits: positions whose rank the next round reads
     size_t scan_tiles = 0;
 
@@ -268,17 +270,56 @@ int run_sort(dark_bwt_ctx* ctx, u64* const keys[2], u32* const vals[2], int cur,
     return 0;
 }
 
-template <bool ROUND0>
-int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32 n, int K, int kb, u32* sa,
-                  u32* out_ids) {
+struct PairSink {  // where a PAIRS re-rank puts its (id, rank) updates
+    u32* ids = nullptr;
+    u32* vals = nullptr;
+    int shift = 0;
+};
+
+template <bool ROUND0, bool PAIRS>
+int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32 n, int K, int kb, u32* sa, u32* out_ids,
+                  PairSink sink = PairSink()) {
     const u32 tiles = (u32)ceil_div(m, kScanTile);
     if (tiles > ctx->scan_tiles) return ctx->fail_internal("scan tile state too small");
     u32* counter = nullptr;
     if (int rc = next_counter(ctx, &counter)) return rc;
     CK(cudaMemsetAsync(ctx->scan_words, 0, sizeof(u64) * kScanWordsPerTile * tiles, ctx->stream));
     ScanTileState ts{ctx->scan_words};
-    k_rerank<kScanThreads, kScanItems, ROUND0><<<tiles, kScanThreads, 0, ctx->stream>>>(
-        keys, ids, m, n, K, kb, ctx->isa, sa, out_ids, ctx->ranks, ts, counter, &ctx->scalars->count);
+    k_rerank<kScanThreads, kScanItems, ROUND0, PAIRS><<<tiles, kScanThreads, 0, ctx->stream>>>(
+        keys, ids, m, n, K, kb, ctx->isa, sa, out_ids, ctx->ranks, ts, counter, &ctx->scalars->count, sink.ids, sink.vals,
+        ctx->bucket_hist, sink.shift);
+    LAUNCHED();
+    return 0;
+}
+
+// Bucketed scatter, step 2 and 3: histogram (already in ctx->bucket_hist) -> cursors, partition the
+// `count` pairs into (out_ids, out_vals), then write isa[] bucket by bucket.
+int bucket_partition(dark_bwt_ctx* ctx, const u32* pair_ids, const u32* pair_vals, u32 count, int shift, u32* out_ids,
+                     u32* out_vals) {
+    const u32 blocks = (u32)ceil_div(count, 256 * 16);
+    if (pair_vals)
+        k_partition_pairs<256, 16, false><<<blocks, 256, 0, ctx->stream>>>(pair_ids, pair_vals, count, shift, ctx->bucket_hist,
+                                                                           out_ids, out_vals);
+    else
+        k_partition_pairs<256, 16, true><<<blocks, 256, 0, ctx->stream>>>(pair_ids, nullptr, count, shift, ctx->bucket_hist,
+                                                                          out_ids, out_vals);
+    LAUNCHED();
+    return 0;
+}
+int bucket_hist_add(dark_bwt_ctx* ctx, const u32* ids, u32 count, int shift) {
+    const u32 blocks = (u32)std::min<u64>(ceil_div(count, 256 * 8), 148 * 8);
+    k_bucket_hist<256><<<std::max(blocks, 1u), 256, 0, ctx->stream>>>(ids, count, shift, ctx->bucket_hist);
+    LAUNCHED();
+    return 0;
+}
+int bucket_scan(dark_bwt_ctx* ctx) {
+    k_bucket_scan<<<1, 256, 0, ctx->stream>>>(ctx->bucket_hist, &ctx->scalars->pair_total);
+    LAUNCHED();
+    return 0;
+}
+int bucket_scatter(dark_bwt_ctx* ctx, const u32* out_ids, const u32* out_vals, u32 upper) {
+    k_scatter_ranks_counted<256><<<(u32)ceil_div(upper, 256), 256, 0, ctx->stream>>>(out_ids, out_vals, &ctx->scalars->pair_total,
+                                                                                      ctx->isa);
     LAUNCHED();
     return 0;
 }
@@ -292,9 +333,25 @@ int fetch_count(dark_bwt_ctx* ctx, u32* out) {
 
 int emit(dark_bwt_ctx* ctx, const u8* d_text, u32 n, const u32* d_sa, u8* d_bwt) {
     const u32 blocks = (u32)ceil_div(ceil_div(n, 4), 256);
-    k_emit_bwt<256><<<blocks, 256, 0, ctx->stream>>>(d_text, n, d_sa, d_bwt, &ctx->scalars->origin,
-                                                      (((uintptr_t)d_bwt) & 3) == 0 ? 1 : 0);
-    LAUNCHED();
+    const bool aligned = (((uintptr_t)d_bwt) & 3) == 0;
+    // text window kept L2-resident per launch (126 MB L2); DARK_BWT_EMIT_WINDOW_MB overrides for sweeps
+    const char* ev = getenv("DARK_BWT_EMIT_WINDOW_MB");
+    const u64 window = (u64)(ev ? std::max(1, atoi(ev)) : 64) << 20;
+    if (!aligned || n <= window + window / 2) {  // small block or odd output pointer: one plain gather launch
+        k_emit_bwt<256><<<blocks, 256, 0, ctx->stream>>>(d_text, n, d_sa, d_bwt, &ctx->scalars->origin, aligned ? 1 : 0);
+        LAUNCHED();
+        return 0;
+    }
+    const u32 nwin = (u32)ceil_div(n, window);
+    const u64 step = ceil_div(n, nwin);
+    for (u32 w = 0; w < nwin; ++w) {
+        const u32 lo = (u32)(w * step), hi = (u32)std::min<u64>((u64)n, (w + 1) * step);
+        if (w == 0)
+            k_emit_bwt_window<256, true><<<blocks, 256, 0, ctx->stream>>>(d_text, n, d_sa, d_bwt, &ctx->scalars->origin, lo, hi);
+        else
+            k_emit_bwt_window<256, false><<<blocks, 256, 0, ctx->stream>>>(d_text, n, d_sa, d_bwt, &ctx->scalars->origin, lo, hi);
+        LAUNCHED();
+    }
     return 0;
 }
 
@@ -406,7 +463,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     const int passes_r = (key_bits + kRadixBits - 1) / kRadixBits;
 
     sp = span_begin(ctx, PH_RERANK);
-    if (int rc = launch_rerank<true>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, Kc, drop, sa, ctx->ids[cur ^ 1])) return rc;
+    if (int rc = launch_rerank<true, false>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, Kc, drop, sa, ctx->ids[cur ^ 1])) return rc;
     span_end(ctx, sp);
     cur ^= 1;  // the compacted active ids now live in ids[cur]
     u32 m = 0;
@@ -416,15 +473,32 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     // survive; otherwise only the survivors' now, and per round the few that are actually read.
     bool isa_complete = true;
     int selective_rounds = 0;
+    // Scatters of more than n/16 ranks into an isa[] that outgrows L2 go through the bucketed path.
+    const char* bev = getenv("DARK_BWT_BUCKETED");
+    const bool bucketed = bev ? atoi(bev) != 0 : ((u64)n * 4 > (96ull << 20));
+    const int bshift = std::max(0, bit_length((u64)n - 1) - 8);
     if (m > 0) {
         sp = span_begin(ctx, PH_RERANK);
         if (m > n / 16) {
-            k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, m, ctx->isa);
+            if (bucketed) {  // every suffix gets its rank: settled ones their slot, survivors their group rank
+                CK(cudaMemsetAsync(ctx->bucket_hist, 0, sizeof(u32) * 256, ctx->stream));
+                if (int rc = bucket_hist_add(ctx, sa, n, bshift)) return rc;
+                if (int rc = bucket_hist_add(ctx, ctx->ids[cur], m, bshift)) return rc;
+                if (int rc = bucket_scan(ctx)) return rc;
+                u32* oi = (u32*)ctx->keys[0];
+                u32* ov = (u32*)ctx->keys[1];
+                if (int rc = bucket_partition(ctx, sa, nullptr, n, bshift, oi, ov)) return rc;
+                if (int rc = bucket_partition(ctx, ctx->ids[cur], ctx->ranks, m, bshift, oi, ov)) return rc;
+                if (int rc = bucket_scatter(ctx, oi, ov, n)) return rc;
+            } else {
+                k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, m, ctx->isa);
+                LAUNCHED();
+            }
         } else {
             k_scatter_ranks<256><<<(u32)ceil_div(m, 256), 256, 0, ctx->stream>>>(ctx->ids[cur], ctx->ranks, m, ctx->isa);
+            LAUNCHED();
             isa_complete = false;
         }
-        LAUNCHED();
         span_end(ctx, sp);
     }
 
@@ -468,7 +542,22 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         span_end(ctx, sp);
 
         sp = span_begin(ctx, PH_RERANK);
-        if (int rc = launch_rerank<false>(ctx, ctx->keys[cur], ctx->ids[cur], m, n, K, kb, sa, ctx->ids[cur ^ 1])) return rc;
+        if (bucketed && m > n / 16) {
+            const size_t ma = align_up((size_t)m, 64);
+            PairSink sink;
+            sink.ids = (u32*)ctx->keys[cur ^ 1];
+            sink.vals = sink.ids + ma;
+            sink.shift = bshift;
+            CK(cudaMemsetAsync(ctx->bucket_hist, 0, sizeof(u32) * 256, ctx->stream));
+            if (int rc = launch_rerank<false, true>(ctx, ctx->keys[cur], ctx->ids[cur], m, n, K, kb, sa, ctx->ids[cur ^ 1], sink)) return rc;
+            if (int rc = bucket_scan(ctx)) return rc;
+            u32* oi = (u32*)ctx->keys[cur];  // the sorted keys are dead once the re-rank has run
+            u32* ov = oi + ma;
+            if (int rc = bucket_partition(ctx, sink.ids, sink.vals, m, bshift, oi, ov)) return rc;
+            if (int rc = bucket_scatter(ctx, oi, ov, m)) return rc;
+        } else {
+            if (int rc = launch_rerank<false, false>(ctx, ctx->keys[cur], ctx->ids[cur], m, n, K, kb, sa, ctx->ids[cur ^ 1])) return rc;
+        }
         span_end(ctx, sp);
         cur ^= 1;
         if (int rc = fetch_count(ctx, &m)) return rc;
@@ -544,7 +633,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
         off = align_up(off + bytes, 256);
         return o;
     };
-    const size_t o_keys0 = carve(N * 8), o_keys1 = carve(N * 8);
+    const size_t o_keys0 = carve(N * 8 + 1024), o_keys1 = carve(N * 8 + 1024);  // slack: pair lists are split at a 64-aligned offset
     const size_t o_ids0 = carve(N * 4 + 16), o_ids1 = carve(N * 4 + 16);
     const size_t o_ranks = carve(N * 4 + 16), o_isa = carve(N * 4 + 16), o_sa = carve(N * 4 + 16);
     const size_t o_text = staging ? carve(N + 16) : 0, o_bwt = staging ? carve(N + 16) : 0;
@@ -554,6 +643,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     const size_t o_scalars = carve(sizeof(DeviceScalars));
     const size_t o_status = carve(ctx->sort_status_bytes);
     const size_t o_counters = carve(sizeof(u32) * kMaxCounters);
+    const size_t o_bhist = carve(sizeof(u32) * 256);
     const size_t o_bitmap = carve(sizeof(u32) * (ceil_div(N, 32) + 1));
     const size_t o_swords = carve(sizeof(u64) * kScanWordsPerTile * ctx->scan_tiles);
     ctx->arena_bytes = off;
@@ -585,6 +675,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     ctx->counters = (u32*)(base + o_counters);
     ctx->scan_words = (u64*)(base + o_swords);
     ctx->bitmap = (u32*)(base + o_bitmap);
+    ctx->bucket_hist = (u32*)(base + o_bhist);
 
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DARK_BWT_E_CUDA);
     if (cudaHostAlloc((void**)&ctx->mail, sizeof(Mailbox), cudaHostAllocDefault) != cudaSuccess) return bail(DARK_BWT_E_NOMEM);

@@ -239,18 +239,25 @@ struct ScanTileState {
 constexpr int kScanWordsPerTile = 4;
 __device__ __forceinline__ u64 scan_pack(u32 flag, u32 value) { return ((u64)flag << 62) | value; }
 
-template <int THREADS, int ITEMS, bool ROUND0>
+// PAIRS (large rounds >= 1): changed ranks are not scattered into isa[] here; element p writes the pair
+// (id, new rank) — (SUF_INVALID, _) if unchanged — to pair_ids[p]/pair_vals[p] and the CTA adds its
+// bucket histogram (id >> pair_shift) to pair_hist for the bucketed scatter that follows.
+template <int THREADS, int ITEMS, bool ROUND0, bool PAIRS>
 __global__ void __launch_bounds__(THREADS)
 k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n, int K, int kb, u32* __restrict__ isa,
          u32* __restrict__ sa, u32* __restrict__ out_ids, u32* __restrict__ out_ranks, ScanTileState ts,
-         u32* __restrict__ tile_counter, u32* __restrict__ out_count) {
+         u32* __restrict__ tile_counter, u32* __restrict__ out_count, u32* __restrict__ pair_ids,
+         u32* __restrict__ pair_vals, u32* __restrict__ pair_hist, int pair_shift) {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
     __shared__ ScanTriple s_warp[WARPS];
     __shared__ ScanTriple s_excl;
     __shared__ u32 s_tile;
+    __shared__ u32 s_bhist[PAIRS ? 256 : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    if (PAIRS)
+        for (int i = tid; i < 256; i += THREADS) s_bhist[i] = 0;
     __syncthreads();
     const u32 tile = s_tile;
     const u64 p0 = (u64)tile * TILE + (u64)tid * ITEMS;  // blocked arrangement
@@ -413,7 +420,14 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
             // Round 0 leaves isa[] alone: if nothing survives (DNA-like blocks) the ranks are never
             // read, otherwise k_round0_isa scatters them afterwards.  It writes every SA slot
             // (SUF_INVALID for unsettled ones) so that kernel can tell which slots are final.
-            if (!ROUND0 && r_new != r_old) isa[sid] = r_new;
+            if (PAIRS) {
+                const bool changed = r_new != r_old;
+                pair_ids[p] = changed ? sid : 0xFFFFFFFFu;
+                pair_vals[p] = r_new;
+                if (changed) atomicAdd(&s_bhist[sid >> pair_shift], 1u);
+            } else if (!ROUND0 && r_new != r_old) {
+                isa[sid] = r_new;
+            }
             if (ROUND0) sa[p] = single ? sid : 0xFFFFFFFFu;
             if (single) {
                 if (!ROUND0) sa[r_new] = sid;
@@ -423,6 +437,11 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
                 run.cnt += 1;
             }
         }
+    }
+    if (PAIRS) {
+        __syncthreads();
+        for (int i = tid; i < 256; i += THREADS)
+            if (s_bhist[i]) atomicAdd(&pair_hist[i], s_bhist[i]);
     }
 }
 
@@ -448,6 +467,13 @@ k_scatter_ranks(const u32* __restrict__ act_ids, const u32* __restrict__ act_ran
     if (p < m) isa[ld_stream(act_ids + p)] = ld_stream(act_ranks + p);
 }
 
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_scatter_ranks_counted(const u32* __restrict__ ids, const u32* __restrict__ vals, const u32* __restrict__ count, u32* __restrict__ isa) {
+    const u64 p = (u64)blockIdx.x * THREADS + threadIdx.x;
+    if (p < *count) isa[ld_stream(ids + p)] = ld_stream(vals + p);
+}
+
 // Selective rank fill (few survivors after round 0): the next round reads isa[i+h] for the
 // active i only, so mark those positions in an n-bit map (L2-resident: n/8 bytes) ...
 template <int THREADS>
@@ -467,6 +493,115 @@ k_fill_needed(const u32* __restrict__ sa, u32 n, const u32* __restrict__ bitmap,
     if (p >= n) return;
     const u32 v = ld_stream(sa + p);
     if (v != 0xFFFFFFFFu && ((__ldg(bitmap + (v >> 5)) >> (v & 31)) & 1u)) isa[v] = (u32)p;
+}
+
+// ---- bucketed rank scatter --------------------------------------------------------------------------
+// isa[id] = rank over ids in SA order is a random 4-byte scatter: every store costs a 32 B sector fill
+// plus write-back once isa[] outgrows L2 (17 GB of DRAM traffic for 2^28 ranks, profiles/r1_ncu_c2_v1.md).
+// Large scatters are therefore done in two steps: (1) partition the (id, rank) pairs by the top 8 bits
+// of id — unstable, so shared-memory atomics give the in-tile position and one global atomicAdd per
+// (tile, bucket) reserves the output run: no look-back chain; (2) scatter bucket by bucket, where
+// each bucket's slice of isa[] (n/256 ranks) stays in L2 and leaves as full sectors.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_bucket_hist(const u32* __restrict__ ids, u32 count, int shift, u32* __restrict__ g_hist) {
+    __shared__ u32 s_hist[256];
+    for (int i = threadIdx.x; i < 256; i += THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * THREADS;
+    for (u64 i = (u64)blockIdx.x * THREADS + threadIdx.x; i < count; i += stride) {
+        const u32 id = ld_stream(ids + i);
+        if (id != 0xFFFFFFFFu) atomicAdd(&s_hist[id >> shift], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += THREADS)
+        if (s_hist[i]) atomicAdd(&g_hist[i], s_hist[i]);
+}
+// counts -> exclusive bases in place (becomes the per-bucket output cursor); total -> *total_out
+__global__ void __launch_bounds__(256) k_bucket_scan(u32* __restrict__ g_hist, u32* __restrict__ total_out) {
+    __shared__ u32 s_warp[8];
+    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    const u32 c = g_hist[d];
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    u32 base = 0;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    g_hist[d] = base + incl - c;
+    if (d == 255) *total_out = base + incl;
+}
+// VAL_IS_INDEX: the value of element i is i itself (rank of a settled suffix = its SA slot).
+template <int THREADS, int ITEMS, bool VAL_IS_INDEX>
+__global__ void __launch_bounds__(THREADS)
+k_partition_pairs(const u32* __restrict__ ids, const u32* __restrict__ vals, u32 count, int shift, u32* __restrict__ cursor,
+                  u32* __restrict__ out_ids, u32* __restrict__ out_vals) {
+    constexpr int TILE = THREADS * ITEMS;
+    __shared__ u32 s_ids[TILE];
+    __shared__ u32 s_vals[TILE];
+    __shared__ u32 s_cnt[256];
+    __shared__ u32 s_start[256];
+    __shared__ u32 s_goff[256];
+    __shared__ u32 s_warp[8];
+    static_assert(THREADS == 256, "one thread per bucket");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    s_cnt[tid] = 0;
+    __syncthreads();
+    const u64 base = (u64)blockIdx.x * TILE;
+    u32 id[ITEMS], val[ITEMS], pos[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u64 i = base + k * THREADS + tid;
+        id[k] = i < count ? ld_stream(ids + i) : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u64 i = base + k * THREADS + tid;
+        val[k] = VAL_IS_INDEX ? (u32)i : (i < count ? ld_stream(vals + i) : 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) pos[k] = id[k] != 0xFFFFFFFFu ? atomicAdd(&s_cnt[id[k] >> shift], 1u) : 0u;
+    __syncthreads();
+    const u32 c = s_cnt[tid];
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    u32 wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+    const u32 start = wbase + incl - c;
+    s_start[tid] = start;
+    s_goff[tid] = (c ? atomicAdd(&cursor[tid], c) : 0u) - start;
+    u32 total = 0;
+    for (int w = 0; w < 8; ++w) total += s_warp[w];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (id[k] != 0xFFFFFFFFu) {
+            const u32 q = s_start[id[k] >> shift] + pos[k];
+            s_ids[q] = id[k];
+            s_vals[q] = val[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const u32 q = k * THREADS + tid;
+        if (q < total) {
+            const u32 v = s_ids[q];
+            const u32 o = s_goff[v >> shift] + q;
+            out_ids[o] = v;
+            out_vals[o] = s_vals[q];
+        }
+    }
 }
 
 // ---- BWT emission ---------------------------------------------------------------------------------
@@ -500,6 +635,64 @@ k_emit_bwt(const u8* __restrict__ text, u32 n, const u32* __restrict__ sa, u8* _
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (j0 + k < n) bwt[j0 + k] = (u8)b[k];
+    }
+}
+
+// Windowed emission for blocks much larger than L2: the gather T[SA[j]-1] is a random one-byte read,
+// and every miss costs a 64 B DRAM granule (92 B per gather measured on C2, profiles/r1_ncu_c2_v1.md).
+// The block is therefore emitted in W launches; launch w serves only the positions that fall into
+// text window w (<= 64 MiB, kept in L2 with an evict_last policy) while SA and the output stream
+// through with evict-first hints.  Each thread owns one aligned 4-byte output word and
+// read-modify-writes it (the first launch writes without reading).
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ u32 ld_u8_keep(const u8* p, u64 pol) {
+    u32 v;
+    asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+template <int THREADS, bool FIRST>
+__global__ void __launch_bounds__(THREADS)
+k_emit_bwt_window(const u8* __restrict__ text, u32 n, const u32* __restrict__ sa, u8* __restrict__ bwt, u64* __restrict__ origin,
+                  u32 win_lo, u32 win_hi) {
+    const u64 j0 = ((u64)blockIdx.x * THREADS + threadIdx.x) * 4;
+    if (j0 >= n) return;
+    const u64 pol = l2_policy_evict_last();
+    u32 s[4];
+    if (j0 + 4 <= n) {
+        uint4 q;
+        asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(sa + j0));
+        s[0] = q.x; s[1] = q.y; s[2] = q.z; s[3] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s[k] = (j0 + k < n) ? sa[j0 + k] : 1u;
+    }
+    u32 pos[4];
+    u32 hit = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        pos[k] = s[k] == 0 ? n - 1 : s[k] - 1;
+        if (j0 + k < n && pos[k] >= win_lo && pos[k] < win_hi) hit |= 1u << k;
+        if (FIRST && s[k] == 0 && j0 + k < n) *origin = j0 + k;
+    }
+    if (!FIRST && hit == 0) return;
+    u32 b[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if ((hit >> k) & 1) b[k] = ld_u8_keep(text + pos[k], pol);
+    const u32 fresh = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+    if (j0 + 4 <= n) {
+        u32* out = reinterpret_cast<u32*>(bwt + j0);
+        u32 word = 0;
+        if (!FIRST && hit != 15u) word = ld_stream(out);
+        st_stream(out, word | fresh);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((hit >> k) & 1) bwt[j0 + k] = (u8)b[k];
     }
 }
 

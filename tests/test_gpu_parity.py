@@ -155,23 +155,39 @@ def test_medium_shapes_vs_oracle_and_fixtures(saca, oracle, golden, torch, key):
     assert np.array_equal(oracle.bwt_decode(bwt, origin), t)
 
 
-def test_u64_status_path_small(oracle):
-    """The 64-bit tile-status variant of the radix pass (used for sorts of >= 2^30 pairs, i.e. the
-    2 GiB block) forced on a small input in a fresh process."""
+FORCED_PATHS = [
+    # (environment that forces a large-block code path on a small input, generator, seed, n)
+    ({"DARK_BWT_FORCE_U64_STATUS": "1"}, "mixed", 4, 300001),       # 64-bit tile status (sorts of >= 2^30 pairs)
+    ({"DARK_BWT_BUCKETED": "1"}, "mixed", 4, 3300001),               # bucketed rank scatter (isa[] larger than L2)
+    ({"DARK_BWT_BUCKETED": "1"}, "rep17", 2, 1500007),
+    ({"DARK_BWT_BUCKETED": "1"}, "dna", 5, 2000003),
+    ({"DARK_BWT_EMIT_WINDOW_MB": "1"}, "mixed", 7, 5000011),         # windowed BWT emission (text larger than L2)
+    ({"DARK_BWT_EMIT_WINDOW_MB": "1", "DARK_BWT_BUCKETED": "1"}, "text", 3, 2500000),
+    ({"DARK_BWT_SORT_VARIANT": "0"}, "mixed", 4, 700001),            # the other radix-pass tilings
+    ({"DARK_BWT_SORT_VARIANT": "3"}, "mixed", 4, 700001),
+    ({"DARK_BWT_SORT_VARIANT": "6"}, "dna", 1, 700001),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(FORCED_PATHS)))
+def test_large_block_code_paths_forced_on_small_inputs(oracle, idx):
+    """Paths that only switch on for huge blocks (64-bit tile status, bucketed rank scatter, windowed
+    emission) are forced through environment knobs in a fresh process and compared with the oracle."""
     import subprocess
     import sys
+    env_extra, kind, seed, n = FORCED_PATHS[idx]
     code = (
         "import numpy as np, oracle\n"
         "from dark_b200 import saca, synth\n"
-        "t = synth.generate('mixed', 4, 300001)\n"
+        f"t = synth.generate('{kind}', {seed}, {n})\n"
         "c = saca.Constructor(t.size)\n"
         "b, o, s = c.bwt_and_sa(t)\n"
         "bo, oo, so = oracle.bwt_forward(t, want_sa=True)\n"
         "assert o == oo and np.array_equal(b, bo) and np.array_equal(s, so)\n"
         "print('ok')\n")
-    env = dict(os.environ, DARK_BWT_FORCE_U64_STATUS="1")
+    env = dict(os.environ, **env_extra)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
