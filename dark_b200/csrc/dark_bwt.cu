@@ -28,7 +28,7 @@ using namespace dark;
 namespace {
 
 constexpr int kSortTile = 3072;  // smallest tile of any pass variant (sizes the status buffer)
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 512;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 constexpr int kInitThreads = 256;

@@ -237,13 +237,14 @@ struct ScanTileState {
     u64* words;  // [tiles][4]  (gs1, hs1, cnt, pad)
 };
 constexpr int kScanWordsPerTile = 4;
+constexpr int kLookbackWarps = 4;  // 128 predecessor tiles polled per look-back step
 __device__ __forceinline__ u64 scan_pack(u32 flag, u32 value) { return ((u64)flag << 62) | value; }
 
 // PAIRS (large rounds >= 1): changed ranks are not scattered into isa[] here; element p writes the pair
 // (id, new rank) — (SUF_INVALID, _) if unchanged — to pair_ids[p]/pair_vals[p] and the CTA adds its
 // bucket histogram (id >> pair_shift) to pair_hist for the bucketed scatter that follows.
 template <int THREADS, int ITEMS, bool ROUND0, bool PAIRS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2)
 k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n, int K, int kb, u32* __restrict__ isa,
          u32* __restrict__ sa, u32* __restrict__ out_ids, u32* __restrict__ out_ranks, ScanTileState ts,
          u32* __restrict__ tile_counter, u32* __restrict__ out_count, u32* __restrict__ pair_ids,
@@ -253,7 +254,11 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
     __shared__ ScanTriple s_warp[WARPS];
     __shared__ ScanTriple s_excl;
     __shared__ u32 s_tile;
+    __shared__ u64 s_lb[2][kLookbackWarps][3];
+    __shared__ u32 s_oid[TILE], s_ork[TILE];  // this tile's survivors, staged for coalesced stores
+    __shared__ u32 s_tile_cnt;
     __shared__ u32 s_bhist[PAIRS ? 256 : 1];
+    static_assert(WARPS >= kLookbackWarps, "look-back warps");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
     if (PAIRS)
@@ -350,20 +355,27 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
     if (lane == 0) texcl = ScanTriple{0u, 0u, 0u};
     texcl = scan_combine(wprefix, texcl);  // exclusive prefix of this thread inside the tile
 
-    // tile aggregate -> publish, look back over a 32-tile window per step (warp 0)
-    if (warp == 0) {
+    // tile aggregate -> publish, look back.  The scan does almost no arithmetic per tile, so every
+    // resident CTA soon waits on its predecessors and throughput becomes (window x tile) elements per
+    // L2 round trip: the "inclusive prefix known" frontier advances one window per polling step.  A
+    // 32-tile window of 2,048-element tiles ran at 1.5-1.9 TB/s (profiles/r1_ncu_c5_c3_v2.md), hence
+    // kLookbackWarps warps poll kLookbackWarps*32 predecessors per step and the tiles are 4,096 wide.
+    if (warp < kLookbackWarps) {
         ScanTriple tile_agg = {0u, 0u, 0u};
         for (int w = 0; w < WARPS; ++w) tile_agg = scan_combine(tile_agg, s_warp[w]);
         ScanTriple excl = {0u, 0u, 0u};
         u64* mine = ts.words + (size_t)tile * kScanWordsPerTile;
         if (tile == 0) {
-            if (lane < 3) st_relaxed(mine + lane, scan_pack(2u, lane == 0 ? tile_agg.gs1 : lane == 1 ? tile_agg.hs1 : tile_agg.cnt));
+            if (warp == 0 && lane < 3)
+                st_relaxed(mine + lane, scan_pack(2u, lane == 0 ? tile_agg.gs1 : lane == 1 ? tile_agg.hs1 : tile_agg.cnt));
         } else {
-            if (lane < 3) st_relaxed(mine + lane, scan_pack(1u, lane == 0 ? tile_agg.gs1 : lane == 1 ? tile_agg.hs1 : tile_agg.cnt));
+            if (warp == 0 && lane < 3)
+                st_relaxed(mine + lane, scan_pack(1u, lane == 0 ? tile_agg.gs1 : lane == 1 ? tile_agg.hs1 : tile_agg.cnt));
             int base = (int)tile - 1;
             u32 pending = 7u;  // bit c set: quantity c has not met an inclusive prefix yet
+            int it = 0;
             while (pending) {
-                const int t = base - lane;
+                const int t = base - (warp * 32 + lane);
                 u64 w0 = scan_pack(2u, 0u), w1 = w0, w2 = w0;  // virtual tiles before tile 0: inclusive identity
                 if (t >= 0) {
                     const u64* theirs = ts.words + (size_t)t * kScanWordsPerTile;
@@ -371,45 +383,72 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
                     do { w1 = ld_relaxed(theirs + 1); } while ((w1 >> 62) == 0);
                     do { w2 = ld_relaxed(theirs + 2); } while ((w2 >> 62) == 0);
                 }
-                // quantity 0: latest old-group head (max)
-                if (pending & 1u) {
+                // per warp: value up to (and including) its nearest inclusive prefix, and whether it has one
+                u64 part0, part1, part2;
+                {
                     const u32 im = __ballot_sync(0xffffffffu, (w0 >> 62) == 2);
                     const int first = im ? (__ffs(im) - 1) : 31;
-                    const u32 v = __reduce_max_sync(0xffffffffu, lane <= first ? (u32)w0 : 0u);
-                    excl.gs1 = max(excl.gs1, v);
-                    if (im) pending &= ~1u;
+                    part0 = (u64)__reduce_max_sync(0xffffffffu, lane <= first ? (u32)w0 : 0u) | (im ? (1ull << 63) : 0ull);
                 }
-                if (pending & 2u) {
+                {
                     const u32 im = __ballot_sync(0xffffffffu, (w1 >> 62) == 2);
                     const int first = im ? (__ffs(im) - 1) : 31;
-                    const u32 v = __reduce_max_sync(0xffffffffu, lane <= first ? (u32)w1 : 0u);
-                    excl.hs1 = max(excl.hs1, v);
-                    if (im) pending &= ~2u;
+                    part1 = (u64)__reduce_max_sync(0xffffffffu, lane <= first ? (u32)w1 : 0u) | (im ? (1ull << 63) : 0ull);
                 }
-                if (pending & 4u) {
+                {
                     const u32 im = __ballot_sync(0xffffffffu, (w2 >> 62) == 2);
                     const int first = im ? (__ffs(im) - 1) : 31;
-                    const u32 v = __reduce_add_sync(0xffffffffu, lane <= first ? (u32)w2 : 0u);
-                    excl.cnt += v;
-                    if (im) pending &= ~4u;
+                    part2 = (u64)__reduce_add_sync(0xffffffffu, lane <= first ? (u32)w2 : 0u) | (im ? (1ull << 63) : 0ull);
                 }
-                base -= 32;
+                if (lane < 3) s_lb[it & 1][warp][lane] = lane == 0 ? part0 : lane == 1 ? part1 : part2;
+                asm volatile("bar.sync 1, %0;" ::"n"(kLookbackWarps * 32) : "memory");
+                // nearest window first; a quantity stops at the first warp that met an inclusive prefix
+#pragma unroll
+                for (int w = 0; w < kLookbackWarps; ++w) {
+                    if (pending & 1u) {
+                        const u64 x = s_lb[it & 1][w][0];
+                        excl.gs1 = max(excl.gs1, (u32)x);
+                        if (x >> 63) pending &= ~1u;
+                    }
+                    if (pending & 2u) {
+                        const u64 x = s_lb[it & 1][w][1];
+                        excl.hs1 = max(excl.hs1, (u32)x);
+                        if (x >> 63) pending &= ~2u;
+                    }
+                    if (pending & 4u) {
+                        const u64 x = s_lb[it & 1][w][2];
+                        excl.cnt += (u32)x;
+                        if (x >> 63) pending &= ~4u;
+                    }
+                }
+                base -= 32 * kLookbackWarps;
+                ++it;
             }
             const ScanTriple inc = scan_combine(excl, tile_agg);
-            if (lane < 3) st_relaxed(mine + lane, scan_pack(2u, lane == 0 ? inc.gs1 : lane == 1 ? inc.hs1 : inc.cnt));
+            if (warp == 0 && lane < 3)
+                st_relaxed(mine + lane, scan_pack(2u, lane == 0 ? inc.gs1 : lane == 1 ? inc.hs1 : inc.cnt));
         }
-        if (lane == 0) {
+        if (warp == 0 && lane == 0) {
             s_excl = excl;
+            s_tile_cnt = tile_agg.cnt;
             if ((u64)(tile + 1) * TILE >= m) *out_count = excl.cnt + tile_agg.cnt;  // last tile: survivors in total
         }
     }
     __syncthreads();
     ScanTriple run = scan_combine(s_excl, texcl);
 
-    // apply
+    // apply.  Stores are shaped for L2: a thread's 8 consecutive words leave as two 128-bit stores,
+    // and the compacted survivors are staged in shared memory and written out lane-consecutively
+    // (per-lane 4-byte stores at a 32 B stride cost one L2 sector operation each; the first version
+    // spent its time there: 3 sector writes per element, profiles/r1_ncu_c5_c3_v2.md).
+    const u32 tile_cnt0 = s_excl.cnt;  // survivors before this tile
+    u32 v_sa[ITEMS], v_pid[ITEMS], v_pval[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const u64 p = p0 + k;
+        v_sa[k] = 0xFFFFFFFFu;
+        v_pid[k] = 0xFFFFFFFFu;
+        v_pval[k] = 0u;
         if (p < m) {
             if ((oldh >> k) & 1) run.gs1 = (u32)p + 1;
             if ((newh >> k) & 1) run.hs1 = (u32)p + 1;
@@ -418,28 +457,67 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
             const u32 sid = id[k + 1];
             const bool single = ((newh >> k) & 1) && ((newh >> (k + 1)) & 1);
             // Round 0 leaves isa[] alone: if nothing survives (DNA-like blocks) the ranks are never
-            // read, otherwise k_round0_isa scatters them afterwards.  It writes every SA slot
-            // (SUF_INVALID for unsettled ones) so that kernel can tell which slots are final.
+            // read, otherwise they are scattered afterwards.  It writes every SA slot
+            // (SUF_INVALID for unsettled ones) so that the later fill can tell which slots are final.
             if (PAIRS) {
                 const bool changed = r_new != r_old;
-                pair_ids[p] = changed ? sid : 0xFFFFFFFFu;
-                pair_vals[p] = r_new;
-                if (changed) atomicAdd(&s_bhist[sid >> pair_shift], 1u);
+                if (changed) {
+                    v_pid[k] = sid;
+                    atomicAdd(&s_bhist[sid >> pair_shift], 1u);
+                }
+                v_pval[k] = r_new;
             } else if (!ROUND0 && r_new != r_old) {
                 isa[sid] = r_new;
             }
-            if (ROUND0) sa[p] = single ? sid : 0xFFFFFFFFu;
+            if (ROUND0 && single) v_sa[k] = sid;
             if (single) {
                 if (!ROUND0) sa[r_new] = sid;
             } else {
-                out_ids[run.cnt] = sid;
-                out_ranks[run.cnt] = r_new;
+                const u32 lq = run.cnt - tile_cnt0;  // position among this tile's survivors
+                s_oid[lq] = sid;
+                s_ork[lq] = r_new;
                 run.cnt += 1;
             }
         }
     }
+    static_assert(ITEMS == 8, "two 128-bit stores per thread");
+    if (ROUND0) {
+        if (p0 + ITEMS <= m && (((uintptr_t)sa) & 15) == 0) {
+            uint4* o = reinterpret_cast<uint4*>(sa + p0);
+            o[0] = make_uint4(v_sa[0], v_sa[1], v_sa[2], v_sa[3]);
+            o[1] = make_uint4(v_sa[4], v_sa[5], v_sa[6], v_sa[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k)
+                if (p0 + k < m) sa[p0 + k] = v_sa[k];
+        }
+    }
     if (PAIRS) {
-        __syncthreads();
+        if (p0 + ITEMS <= m) {
+            uint4* o = reinterpret_cast<uint4*>(pair_ids + p0);
+            o[0] = make_uint4(v_pid[0], v_pid[1], v_pid[2], v_pid[3]);
+            o[1] = make_uint4(v_pid[4], v_pid[5], v_pid[6], v_pid[7]);
+            uint4* q = reinterpret_cast<uint4*>(pair_vals + p0);
+            q[0] = make_uint4(v_pval[0], v_pval[1], v_pval[2], v_pval[3]);
+            q[1] = make_uint4(v_pval[4], v_pval[5], v_pval[6], v_pval[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k)
+                if (p0 + k < m) {
+                    pair_ids[p0 + k] = v_pid[k];
+                    pair_vals[p0 + k] = v_pval[k];
+                }
+        }
+    }
+    __syncthreads();
+    {
+        const u32 tile_cnt = s_tile_cnt;
+        for (u32 i = tid; i < tile_cnt; i += THREADS) {
+            out_ids[tile_cnt0 + i] = s_oid[i];
+            out_ranks[tile_cnt0 + i] = s_ork[i];
+        }
+    }
+    if (PAIRS) {
         for (int i = tid; i < 256; i += THREADS)
             if (s_bhist[i]) atomicAdd(&pair_hist[i], s_bhist[i]);
     }
