@@ -94,6 +94,7 @@ struct dark_bwt_ctx {
     size_t sort_status_bytes = 0;
     u32* counters = nullptr;
     u64* scan_words = nullptr;
+    long long* pass_trace = nullptr;  // debug: per-tile phase stamps of the radix pass (dark_bwt_debug_trace)
     u32* bucket_hist = nullptr;  // 256 counters / cursors of the bucketed rank scatter
     u32* bitmap = nullptr;  // n bits: positions whose rank the next round reads
     size_t scan_tiles = 0;
@@ -163,6 +164,19 @@ int next_counter(dark_bwt_ctx* ctx, u32** out) {
 
 // Tuning variants of the radix pass (threads, items per thread, min CTAs per SM).  The default is
 // chosen from measurements (profiles/); DARK_BWT_SORT_VARIANT=<i> selects another one for sweeps.
+template <int THREADS, int ITEMS, int MINBLOCKS, typename StatusT, bool ALIGNED>
+int launch_pass_kernel(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
+                       const u32* digit_base, u32* counter, u32 tiles) {
+    typedef OnesweepSmem<THREADS, ITEMS> Smem;
+    auto kern = k_onesweep_pass<THREADS, ITEMS, MINBLOCKS, StatusT, ALIGNED>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));  // per device
+    static const bool by_block_index = getenv("DARK_BWT_TILE_BY_BLOCKIDX") != nullptr;
+    kern<<<tiles, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base, (StatusT*)ctx->sort_status,
+                                                        by_block_index ? nullptr : counter, ctx->pass_trace);
+    LAUNCHED();
+    return 0;
+}
+
 template <int THREADS, int ITEMS, int MINBLOCKS>
 int launch_pass_variant(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
                         const u32* digit_base, u32* counter, bool wide) {
@@ -171,22 +185,16 @@ int launch_pass_variant(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* 
     const size_t bytes = (size_t)tiles * kRadix * (wide ? sizeof(u64) : sizeof(u32));
     if (bytes > ctx->sort_status_bytes) return ctx->fail_internal("sort status buffer too small");
     CK(cudaMemsetAsync(ctx->sort_status, 0, bytes, ctx->stream));
+    const bool aligned = (shift & 7) == 0;  // always true for the suffix sorter; the public sort may differ
     if (!wide) {
-        auto kern = k_onesweep_pass<THREADS, ITEMS, MINBLOCKS, u32>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));  // per device
-        kern<<<tiles, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base,
-                                                            (u32*)ctx->sort_status, counter);
-    } else {
-        auto kern = k_onesweep_pass<THREADS, ITEMS, MINBLOCKS, u64>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));  // per device
-        kern<<<tiles, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base,
-                                                            (u64*)ctx->sort_status, counter);
+        if (aligned) return launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, u32, true>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, tiles);
+        return launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, u32, false>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, tiles);
     }
-    LAUNCHED();
-    return 0;
+    if (aligned) return launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, u64, true>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, tiles);
+    return launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, u64, false>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, tiles);
 }
 
-constexpr int kDefaultSortVariant = 5;  // 512 threads x 12 items, 2 CTAs/SM: best of the sweep in profiles/r1_sort_variants_v2.log
+constexpr int kDefaultSortVariant = 1;  // 256 threads x 16 items, 3 CTAs/SM: best of the sweeps in profiles/r1_sort_variants_*.log
 
 // One onesweep pass over m pairs: buffers[cur] -> buffers[cur^1].
 int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
@@ -200,18 +208,12 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
     const int variant = ev ? atoi(ev) : kDefaultSortVariant;
 #define V(T, I, B) return launch_pass_variant<T, I, B>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide)
     switch (variant) {
-        case 1: V(256, 16, 3);
-        case 2: V(512, 8, 2);
+        case 0: V(256, 16, 2);
+        case 2: V(256, 12, 3);
         case 3: V(512, 8, 3);
-        case 4: V(384, 12, 2);
         case 5: V(512, 12, 2);
-        case 6: V(256, 12, 3);
-        case 7: V(1024, 4, 1);
-        case 8: V(256, 8, 4);
-        case 9: V(256, 8, 5);
         case 10: V(512, 10, 2);
-        case 11: V(512, 14, 2);
-        default: V(256, 16, 2);
+        default: V(256, 16, 3);  // 1
     }
 #undef V
 }
@@ -802,6 +804,14 @@ int dark_bwt_verify_sa_device(dark_bwt_ctx* ctx, const uint8_t* d_text, uint64_t
     CK(cudaMemcpyAsync(&ctx->mail->bad, &ctx->scalars->bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     *bad_out = ctx->mail->bad;
+    return DARK_BWT_OK;
+}
+
+// Debug hook (not in the public header): per-tile clock64() stamps of subsequent radix passes are
+// written to d_trace ([tiles][8] long long); nullptr switches tracing off.
+int dark_bwt_debug_trace(dark_bwt_ctx* ctx, long long* d_trace) {
+    if (!ctx) return DARK_BWT_E_INVALID_ARG;
+    ctx->pass_trace = d_trace;
     return DARK_BWT_OK;
 }
 

@@ -108,6 +108,7 @@ struct OnesweepSmem {
     static constexpr int kWarps = THREADS / 32;
     u64 keys[kTile];             // tile re-ordered by digit (so the global scatter is run-coalesced)
     u32 vals[kTile];
+    u32 raw_vals[kTile];         // values as loaded (cp.async), consumed by the re-order
     u32 warp_hist[kWarps][kRadix];  // per-warp digit counters -> exclusive warp offsets
     u32 digit_start[kRadix];        // exclusive scan of the tile's digit counts
     u32 global_off[kRadix];         // output index of local position 0 of each digit (mod 2^32)
@@ -115,85 +116,95 @@ struct OnesweepSmem {
     u32 tile;
 };
 
-template <int THREADS, int ITEMS, int MINBLOCKS, typename StatusT>
-__global__ void __launch_bounds__(THREADS, MINBLOCKS)
-k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
-                u32* __restrict__ vals_out, u32 m, int shift, const u32* __restrict__ digit_base,
-                StatusT* __restrict__ status, u32* __restrict__ tile_counter) {
-    static_assert(THREADS >= kRadix && THREADS % 32 == 0, "one thread per digit is assumed");
+// Digit selection.  ALIGNED (shift a multiple of 8, the only case the suffix sorter uses): the digit
+// is one byte of the high or low key word, a single PRMT.  Otherwise a generic 64-bit shift.
+template <bool ALIGNED>
+struct DigitSel {
+    int shift;
+    u32 bsel;  // __byte_perm selector: 0x4440 | byte index inside the word
+    bool hi;
+    __device__ __forceinline__ explicit DigitSel(int sh) : shift(sh), bsel(0x4440u | ((u32)(sh & 31) >> 3)), hi(sh >= 32) {}
+    __device__ __forceinline__ u32 operator()(u64 key) const {
+        if (ALIGNED) {
+            const u32 w = hi ? (u32)(key >> 32) : (u32)key;  // `hi` is launch-uniform
+            return __byte_perm(w, 0u, bsel);
+        }
+        return (u32)(key >> shift) & (kRadix - 1);
+    }
+};
+
+// The body of one tile.  FULL = all THREADS*ITEMS slots hold a pair (every tile but the last):
+// no validity predicates anywhere on that path.
+template <int THREADS, int ITEMS, typename StatusT, bool ALIGNED, bool FULL>
+__device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, const u64* __restrict__ keys_in,
+                                              const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
+                                              u32* __restrict__ vals_out, const u32 tile, const u32 nvalid, const int shift,
+                                              const u32* __restrict__ digit_base, StatusT* __restrict__ status,
+                                              long long* __restrict__ trace) {
+    // trace != nullptr (tools/pass_trace.py only): thread 0 stamps clock64() at the phase boundaries
+#define DARK_STAMP(i) do { if (trace && threadIdx.x == 0) trace[(size_t)tile * 8 + (i)] = clock64(); } while (0)
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
     typedef StatusTraits<StatusT> ST;
     constexpr int TILE = Smem::kTile;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    // Tiles are claimed in launch order so that every predecessor of a tile is already running:
-    // the look-back below never waits on a CTA that has not been scheduled.
-    if (tid == 0) s.tile = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < Smem::kWarps * kRadix; i += THREADS) (&s.warp_hist[0][0])[i] = 0;
-    __syncthreads();
-    const u32 tile = s.tile;
     const u64 tile_base = (u64)tile * TILE;
-    const u32 nvalid = (u32)min((u64)TILE, (u64)m - tile_base);
+    const DigitSel<ALIGNED> digit(shift);
 
     // warp-striped arrangement: element (warp, k, lane) has tile-local index warp*32*ITEMS + k*32 + lane,
     // so every load instruction of a warp covers 32 consecutive pairs and rank order == index order.
     const u32 local0 = warp * (32 * ITEMS) + lane;
+    const u64* kp = keys_in + tile_base + local0;
     u64 key[ITEMS];
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const u32 li = local0 + k * 32;
-        key[k] = (li < nvalid) ? ld_stream(keys_in + tile_base + li) : ~0ull;
+    for (int k = 0; k < ITEMS; ++k) key[k] = (FULL || local0 + k * 32 < nvalid) ? ld_stream(kp + k * 32) : ~0ull;
+    // The values go straight to shared memory with cp.async (no registers held across the ranking
+    // loop, latency hidden behind it); each thread later reads back exactly the words it copied.
+    {
+        const u32* vp = vals_in + tile_base + local0;
+        const u32 dst = smem_addr(&s.raw_vals[local0]);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k)
+            if (FULL || local0 + k * 32 < nvalid)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + k * 128), "l"(vp + k * 32) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
-    // ---- rank inside the warp: lanes with equal digits are found with 8 ballots (one per digit
-    // bit; the match.any instruction is microcoded per distinct value and was the top stall of the
-    // first version, profiles/r1_ncu_c2_v1.md); the lowest lane of each group bumps the counter.
-    static_assert(ITEMS % 2 == 0, "ranks are packed two per register");
-    u32 rank2[ITEMS / 2];  // 16-bit ranks (< 32*ITEMS), two per register
+    // ---- rank inside the warp.  Lanes with equal digits are found with 8 ballots (one per digit bit;
+    // match.any is microcoded per distinct value and was the top stall of the first version,
+    // profiles/r1_ncu_c2_v1.md).  Every lane reads its digit's counter, the lowest lane of each group
+    // then bumps it.  Ranks are < 32*ITEMS and packed two per register.
+    static_assert(ITEMS % 2 == 0 && 32 * ITEMS < 65536, "ranks are packed two per register");
+    u32 rank2[ITEMS / 2];
     u32* whist = s.warp_hist[warp];
     const u32 lt = lanemask_lt();
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-        const bool valid = (local0 + k * 32) < nvalid;
-        u32 d = digit_of(key[k], shift);
+        const bool valid = FULL || (local0 + k * 32) < nvalid;
+        u32 d = digit(key[k]);
         // Tie this item's ballots to the result of item k-2: without the false dependency the
         // compiler hoists the votes of all ITEMS items to the top (150+ registers, one CTA per SM).
         if (k >= 2) asm volatile("" : "+r"(d) : "r"(rank2[(k - 2) / 2]));
-        u32 peers = __ballot_sync(0xffffffffu, valid);
+        u32 peers = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
 #pragma unroll
         for (int b = 0; b < kRadixBits; ++b) {
             const bool bit = (d >> b) & 1u;
             const u32 vote = __ballot_sync(0xffffffffu, bit);
             peers &= bit ? vote : ~vote;
         }
-        if (!valid) peers = 1u << lane;  // padding lanes stand alone and count nothing
-        const int leader = __ffs(peers) - 1;
-        u32 prev = 0;
-        if (lane == leader && valid) {
-            prev = whist[d];
-            whist[d] = prev + __popc(peers);
-        }
-        prev = __shfl_sync(0xffffffffu, prev, leader);
-        const u32 r = prev + __popc(peers & lt);
+        const u32 prev = whist[d];  // every lane reads (padding lanes harmlessly), then the group's lowest lane bumps
+        const u32 below = peers & lt;
+        const u32 r = prev + __popc(below);
+        __syncwarp();
+        if (valid && below == 0) whist[d] = prev + __popc(peers);
         if (k & 1) rank2[k / 2] |= r << 16;
         else rank2[k / 2] = r;
         __syncwarp();
     }
+    DARK_STAMP(2);
     __syncthreads();
+    DARK_STAMP(3);
 
-    // values are fetched only now, so they do not occupy registers during the ranking loop; their
-    // latency overlaps the digit scan below
-    u32 val[ITEMS];
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const u32 li = local0 + k * 32;
-        val[k] = (li < nvalid) ? ld_stream(vals_in + tile_base + li) : 0u;
-    }
-
-    // ---- per-digit: exclusive offsets across warps, tile total, publish, look back
+    // ---- per digit: exclusive offsets across warps, tile total, publish the aggregate
     u32 count = 0;
     if (tid < kRadix) {
         u32 run = 0;
@@ -204,8 +215,7 @@ k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in
             run += c;
         }
         count = run;
-        StatusT* slot = status + (size_t)tile * kRadix + tid;
-        st_relaxed(slot, ((StatusT)(tile == 0 ? 2 : 1) << ST::kShift) | (StatusT)count);
+        st_relaxed(status + (size_t)tile * kRadix + tid, ((StatusT)(tile == 0 ? 2 : 1) << ST::kShift) | (StatusT)count);
     }
     // exclusive scan of the 256 digit counts (threads >= 256 contribute 0 and are ignored)
     u32 incl = count;
@@ -221,52 +231,111 @@ k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in
         u32 wbase = 0;
         for (int w = 0; w < warp; ++w) wbase += s.warp_sum[w];
         dstart = wbase + incl - count;
-        s.digit_start[tid] = dstart;
+        // fold the digit start into the per-warp offsets: one table lookup per element in the re-order
+#pragma unroll
+        for (int w = 0; w < Smem::kWarps; ++w) s.warp_hist[w][tid] += dstart;
     }
     __syncthreads();
+    DARK_STAMP(4);
 
     // ---- re-order the tile by digit in shared memory (needs only tile-local offsets, so it runs
     // before the look-back and gives the predecessor tiles time to publish)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-        if ((local0 + k * 32) < nvalid) {
-            const u32 d = digit_of(key[k], shift);
-            const u32 pos = s.digit_start[d] + whist[d] + ((rank2[k / 2] >> (16 * (k & 1))) & 0xFFFFu);
+        if (FULL || (local0 + k * 32) < nvalid) {
+            const u32 pos = whist[digit(key[k])] + ((rank2[k / 2] >> (16 * (k & 1))) & 0xFFFFu);
             s.keys[pos] = key[k];
-            s.vals[pos] = val[k];
+            s.vals[pos] = s.raw_vals[local0 + k * 32];
         }
     }
 
+    DARK_STAMP(5);
     // ---- decoupled look-back over the predecessors' digit counts
     if (tid < kRadix) {
         StatusT excl = 0;
         if (tile > 0) {
+            // Tiles finish every ~60 cycles chip-wide while one status read costs an L2 round trip
+            // (~600 cycles), so the nearest inclusive prefix is typically 10-15 tiles back: walking
+            // them one load at a time cost 34 % of the tile time (tools/pass_trace.py,
+            // profiles/r1_pass_trace_v3.log).  Read kLookbackBatch predecessors per round trip instead.
+            constexpr int kLookbackBatch = 8;
             int t = (int)tile - 1;
-            for (;;) {
-                const StatusT v = ld_relaxed(status + (size_t)t * kRadix + tid);
-                const u32 flag = (u32)(v >> ST::kShift);
-                if (flag == 0) continue;  // predecessor has not published yet
-                excl += v & ST::kMask;
-                if (flag == 2) break;
-                --t;
+            bool found = false;
+            while (!found) {
+                StatusT v[kLookbackBatch];
+#pragma unroll
+                for (int j = 0; j < kLookbackBatch; ++j)
+                    v[j] = (t - j >= 0) ? ld_relaxed(status + (size_t)(t - j) * kRadix + tid) : ((StatusT)2 << ST::kShift);
+                int used = kLookbackBatch;
+#pragma unroll
+                for (int j = 0; j < kLookbackBatch; ++j) {
+                    if (j < used && !found) {
+                        const u32 flag = (u32)(v[j] >> ST::kShift);
+                        if (flag == 0) {
+                            used = j;  // not published yet: poll again from this tile
+                        } else {
+                            excl += v[j] & ST::kMask;
+                            if (flag == 2) found = true;
+                        }
+                    }
+                }
+                t -= used;
             }
             st_relaxed(status + (size_t)tile * kRadix + tid, ((StatusT)2 << ST::kShift) | (excl + count));
         }
         s.global_off[tid] = digit_base[tid] + (u32)excl - dstart;
     }
     __syncthreads();
+    DARK_STAMP(6);
 
     // ---- scatter: consecutive threads write consecutive addresses inside each digit run
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const u32 p = k * THREADS + tid;
-        if (p < nvalid) {
+        if (FULL || p < nvalid) {
             const u64 kk = s.keys[p];
-            const u32 idx = s.global_off[digit_of(kk, shift)] + p;
+            const u32 idx = s.global_off[digit(kk)] + p;
             keys_out[idx] = kk;
             vals_out[idx] = s.vals[p];
         }
     }
+    DARK_STAMP(7);
+#undef DARK_STAMP
+}
+
+template <int THREADS, int ITEMS, int MINBLOCKS, typename StatusT, bool ALIGNED>
+__global__ void __launch_bounds__(THREADS, MINBLOCKS)
+k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
+                u32* __restrict__ vals_out, u32 m, int shift, const u32* __restrict__ digit_base,
+                StatusT* __restrict__ status, u32* __restrict__ tile_counter, long long* __restrict__ trace) {
+    static_assert(THREADS >= kRadix && THREADS % 32 == 0, "one thread per digit is assumed");
+    typedef OnesweepSmem<THREADS, ITEMS> Smem;
+    constexpr int TILE = Smem::kTile;
+    const long long t_entry = trace ? clock64() : 0;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x;
+
+    // Tile order.  The look-back only waits on lower-numbered tiles, so those must already be running.
+    // By default tiles are claimed from a counter in the order CTAs actually start (one L2 atomic
+    // round trip before the first load can be issued).  With tile_counter == nullptr the tile is
+    // blockIdx.x, relying on the hardware dispatching CTAs of a 1-D grid in index order.
+    if (tile_counter != nullptr && tid == 0) s.tile = atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < Smem::kWarps * kRadix; i += THREADS) (&s.warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const u32 tile = tile_counter != nullptr ? s.tile : blockIdx.x;
+    if (trace && tid == 0) {
+        trace[(size_t)tile * 8 + 0] = t_entry;
+        trace[(size_t)tile * 8 + 1] = clock64();
+    }
+    const u32 nvalid = (u32)min((u64)TILE, (u64)m - (u64)tile * TILE);
+    if (nvalid == TILE)
+        onesweep_tile<THREADS, ITEMS, StatusT, ALIGNED, true>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid, shift,
+                                                              digit_base, status, trace);
+    else
+        onesweep_tile<THREADS, ITEMS, StatusT, ALIGNED, false>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid, shift,
+                                                               digit_base, status, trace);
 }
 
 }  // namespace dark
