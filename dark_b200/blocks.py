@@ -18,9 +18,9 @@ def all_shards(num_blocks, world_size):
 
 
 def bwt_blocks(constructor, blocks):
-    """Run the forward BWT over an iterable of host blocks on one context; yields (bwt, origin)."""
-    for blk in blocks:
-        yield constructor.bwt(blk)
+    """Forward BWT of an iterable of host blocks on one context -> [(bwt, origin), ...], using the
+    pipelined batch entry (copies overlap the transforms)."""
+    return constructor.bwt_blocks(list(blocks))
 
 
 def aggregate(ms_local, units_local, group=None):

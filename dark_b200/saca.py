@@ -91,6 +91,28 @@ class Constructor:
                                             ctypes.byref(self.stats)), self._ctx, "Constructor::bwt")
         return int(origin.value)
 
+    def bwt_batch_into(self, text_ptrs, ns, bwt_ptrs, want_stats=False):
+        """Pipelined host entry over several blocks (raw host addresses, ideally pinned):
+        copy-in of block k+1 and copy-out of block k-1 overlap the transform of block k.
+        Returns the list of origins (and the per-block stats if asked)."""
+        cnt = len(ns)
+        assert len(text_ptrs) == cnt and len(bwt_ptrs) == cnt
+        T = (ctypes.c_void_p * cnt)(*text_ptrs)
+        B = (ctypes.c_void_p * cnt)(*bwt_ptrs)
+        N = (ctypes.c_uint64 * cnt)(*[int(x) for x in ns])
+        O = (ctypes.c_uint64 * cnt)()
+        S = (_ffi.Stats * cnt)() if want_stats else None
+        _ffi.check(self._L.dark_bwt_forward_batch(self._ctx, T, N, B, O, None, cnt, S), self._ctx, "Constructor::bwt_batch")
+        origins = [int(O[i]) for i in range(cnt)]
+        return (origins, [S[i].as_dict() for i in range(cnt)]) if want_stats else origins
+
+    def bwt_blocks(self, blocks):
+        """[(bwt, origin), ...] for an iterable of host blocks, through the pipelined batch entry."""
+        ts = [_as_u8(b) for b in blocks]
+        outs = [np.empty(t.size, dtype=np.uint8) for t in ts]
+        origins = self.bwt_batch_into([t.ctypes.data for t in ts], [t.size for t in ts], [o.ctypes.data for o in outs])
+        return list(zip(outs, origins))
+
     # -- device-resident form (benches, pipelines that keep the block in HBM) ------------------
     def bwt_device(self, d_text, n, d_bwt, d_sa=None):
         """Raw device pointers (ints).  Returns origin; self.stats holds the device timings."""

@@ -105,6 +105,15 @@ uint64_t dark_bwt_capacity(const dark_bwt_ctx *ctx);
 int dark_bwt_forward(dark_bwt_ctx *ctx, const uint8_t *text, uint64_t n, uint8_t *bwt_out, uint64_t *origin_out,
                      uint32_t *sa_out, dark_bwt_stats *stats);
 
+/* `count` independent host blocks through one context, pipelined: while block k is transformed, block
+ * k+1 is copied in and block k-1 is copied out (two copy streams beside the compute stream, double-
+ * buffered device staging).  This is how a corpus of blocks is fed — the reference encodes one block
+ * per Encoder (src/main.rs:95-113) and blocks share nothing.  Pinned host buffers overlap fully;
+ * pageable ones still work.  sa_outs and stats are nullable (entries of sa_outs too); stats, if
+ * given, is an array of `count` records.  Results are identical to `count` dark_bwt_forward calls. */
+int dark_bwt_forward_batch(dark_bwt_ctx *ctx, const uint8_t *const *texts, const uint64_t *ns, uint8_t *const *bwt_outs,
+                           uint64_t *origins_out, uint32_t *const *sa_outs, uint64_t count, dark_bwt_stats *stats);
+
 /* Same on DEVICE buffers (d_text, d_bwt_out, d_sa_out live on the context's device;
  * d_sa_out nullable; origin_out and stats are host pointers).  No readable slack after
  * d_text[n-1] is required.  Returns after the work has completed on the stream. */

@@ -41,6 +41,8 @@ extern "C" {
     pub fn dark_bwt_capacity(ctx: *const dark_bwt_ctx) -> u64;
     pub fn dark_bwt_forward(ctx: *mut dark_bwt_ctx, text: *const u8, n: u64, bwt_out: *mut u8,
                             origin_out: *mut u64, sa_out: *mut u32, stats: *mut dark_bwt_stats) -> c_int;
+    pub fn dark_bwt_forward_batch(ctx: *mut dark_bwt_ctx, texts: *const *const u8, ns: *const u64, bwt_outs: *const *mut u8,
+                                  origins_out: *mut u64, sa_outs: *const *mut u32, count: u64, stats: *mut dark_bwt_stats) -> c_int;
     pub fn dark_bwt_forward_device(ctx: *mut dark_bwt_ctx, d_text: *const u8, n: u64, d_bwt_out: *mut u8,
                                    origin_out: *mut u64, d_sa_out: *mut u32, stats: *mut dark_bwt_stats) -> c_int;
     pub fn dark_bwt_reuse(ctx: *mut dark_bwt_ctx, words_out: *mut *mut u32, count_out: *mut u64) -> c_int;

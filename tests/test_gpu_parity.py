@@ -289,6 +289,30 @@ def test_large_shapes_vs_fixtures_device_resident(saca, golden, torch, key):
     con.close()
 
 
+def test_pipelined_batch_entry_matches_single_calls(saca, oracle, torch):
+    """dark_bwt_forward_batch: several blocks of different shapes and sizes through the double-buffered
+    copy/compute pipeline give exactly what separate calls (and the oracle) give."""
+    from dark_b200 import synth
+    con = saca.Constructor(1 << 21)
+    specs = [("mixed", 6, 1 << 21), ("dna", 3, 999983), ("text", 4, 12345), ("rep17", 5, 1 << 20), ("dna", 8, 2),
+             ("mixed", 11, (1 << 21) - 1), ("text", 12, 300000)]
+    blocks = [synth.generate(k, s, n) for k, s, n in specs]
+    res = con.bwt_blocks(blocks)
+    assert len(res) == len(blocks)
+    for blk, (bwt, origin) in zip(blocks, res):
+        bwt_o, origin_o = oracle.bwt_forward(blk)
+        assert origin == origin_o and np.array_equal(bwt, bwt_o)
+    # pinned buffers, repeated block, alternating outputs (what bench.py does)
+    t = torch.from_numpy(blocks[0]).pin_memory()
+    o1 = torch.empty(t.numel(), dtype=torch.uint8).pin_memory()
+    o2 = torch.empty(t.numel(), dtype=torch.uint8).pin_memory()
+    origins, stats = con.bwt_batch_into([t.data_ptr()] * 5, [t.numel()] * 5, [o1.data_ptr(), o2.data_ptr()] * 2 + [o1.data_ptr()],
+                                        want_stats=True)
+    assert origins == [res[0][1]] * 5 and len(stats) == 5
+    assert np.array_equal(o1.numpy(), res[0][0]) and np.array_equal(o2.numpy(), res[0][0])
+    con.close()
+
+
 def test_idempotent_context_reuse(saca, oracle, torch):
     """One context, many blocks of different sizes (the Encoder keeps its Constructor)."""
     from dark_b200 import synth
