@@ -73,6 +73,7 @@ inline int bit_length(u64 x) {
 
 struct dark_bwt_ctx {
     int device = 0;
+    int num_sms = 148;
     u64 capacity = 0;
     u32 flags = 0;
     cudaStream_t stream = nullptr;
@@ -169,20 +170,22 @@ int next_counter(dark_bwt_ctx* ctx, u32** out) {
 
 // Tuning variants of the radix pass (threads, items per thread, min CTAs per SM).  The default is
 // chosen from measurements (profiles/); DARK_BWT_SORT_VARIANT=<i> selects another one for sweeps.
-template <int THREADS, int ITEMS, int MINBLOCKS, typename StatusT, bool ALIGNED>
+template <int THREADS, int ITEMS, int MINBLOCKS, int ILP, typename StatusT, bool ALIGNED>
 int launch_pass_kernel(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
                        const u32* digit_base, u32* counter, u32 tiles) {
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
-    auto kern = k_onesweep_pass<THREADS, ITEMS, MINBLOCKS, StatusT, ALIGNED>;
+    auto kern = k_onesweep_pass<THREADS, ITEMS, MINBLOCKS, ILP, StatusT, ALIGNED>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));  // per device
     static const bool by_block_index = getenv("DARK_BWT_TILE_BY_BLOCKIDX") != nullptr;
-    kern<<<tiles, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base, (StatusT*)ctx->sort_status,
+    // persistent grid: as many CTAs as stay resident (SMs x MINBLOCKS), each claiming tiles until none are left
+    const u32 grid = by_block_index ? tiles : std::min<u32>(tiles, (u32)ctx->num_sms * MINBLOCKS);
+    kern<<<grid, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base, (StatusT*)ctx->sort_status,
                                                         by_block_index ? nullptr : counter, ctx->pass_trace);
     LAUNCHED();
     return 0;
 }
 
-template <int THREADS, int ITEMS, int MINBLOCKS>
+template <int THREADS, int ITEMS, int MINBLOCKS, int ILP>
 int launch_pass_variant(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
                         const u32* digit_base, u32* counter, bool wide) {
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
@@ -191,12 +194,10 @@ int launch_pass_variant(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* 
     if (bytes > ctx->sort_status_bytes) return ctx->fail_internal("sort status buffer too small");
     CK(cudaMemsetAsync(ctx->sort_status, 0, bytes, ctx->stream));
     const bool aligned = (shift & 7) == 0;  // always true for the suffix sorter; the public sort may differ
-    if (!wide) {
-        if (aligned) return launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, u32, true>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, tiles);
-        return launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, u32, false>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, tiles);
-    }
-    if (aligned) return launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, u64, true>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, tiles);
-    return launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, u64, false>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, tiles);
+#define LP(ST, AL) launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, ILP, ST, AL>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, tiles)
+    if (!aligned) return wide ? LP(u64, false) : LP(u32, false);
+    return wide ? LP(u64, true) : LP(u32, true);
+#undef LP
 }
 
 constexpr int kDefaultSortVariant = 1;  // 256 threads x 16 items, 3 CTAs/SM: best of the sweeps in profiles/r1_sort_variants_*.log
@@ -211,14 +212,12 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
     const bool wide = !(m < (1u << 30)) || getenv("DARK_BWT_FORCE_U64_STATUS") != nullptr;
     const char* ev = getenv("DARK_BWT_SORT_VARIANT");
     const int variant = ev ? atoi(ev) : kDefaultSortVariant;
-#define V(T, I, B) return launch_pass_variant<T, I, B>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide)
+#define V(T, I, B, L) return launch_pass_variant<T, I, B, L>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide)
     switch (variant) {
-        case 0: V(256, 16, 2);
-        case 2: V(256, 12, 3);
-        case 3: V(512, 8, 3);
-        case 5: V(512, 12, 2);
-        case 10: V(512, 10, 2);
-        default: V(256, 16, 3);  // 1
+        case 0: V(256, 16, 2, 2);
+        case 2: V(256, 12, 3, 2);
+        case 5: V(512, 12, 2, 2);
+        default: V(256, 16, 3, 2);  // 1
     }
 #undef V
 }
@@ -349,7 +348,9 @@ int emit(dark_bwt_ctx* ctx, const u8* d_text, u32 n, const u32* d_sa, u8* d_bwt)
         LAUNCHED();
         return 0;
     }
-    const u32 nwin = (u32)ceil_div(n, window);
+    // every window launch re-reads the whole SA (4n bytes), so the window count is capped: beyond 8
+    // windows (blocks over 512 MiB) they grow past L2 instead (C4: 32 windows cost 93 ms)
+    const u32 nwin = (u32)std::min<u64>(ceil_div(n, window), 8);
     const u64 step = ceil_div(n, nwin);
     for (u32 w = 0; w < nwin; ++w) {
         const u32 lo = (u32)(w * step), hi = (u32)std::min<u64>((u64)n, (w + 1) * step);
@@ -623,6 +624,10 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     dark_bwt_ctx* ctx = new (std::nothrow) dark_bwt_ctx();
     if (!ctx) return DARK_BWT_E_NOMEM;
     ctx->device = device;
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->num_sms = sms;
+    }
     ctx->capacity = max_n;
     ctx->flags = flags;
 

@@ -116,6 +116,36 @@ struct OnesweepSmem {
     u32 tile;
 };
 
+// Lanes whose 8-bit digit equals mine, restricted to `peers`: one test + one vote + a predicated NOT +
+// an AND per bit.  Written in PTX because the C++ form (`bit ? vote : ~vote`) compiled to 6 instructions
+// per bit (bit tested twice, a SEL to build the mask).
+template <int BIT>
+__device__ __forceinline__ u32 match_digit_bit(u32 peers, u32 d) {
+    asm("{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 v;\n"
+        "and.b32 v, %1, %2;\n"
+        "setp.ne.u32 p, v, 0;\n"
+        "vote.sync.ballot.b32 v, p, 0xffffffff;\n"
+        "@!p not.b32 v, v;\n"
+        "and.b32 %0, %0, v;\n"
+        "}\n"
+        : "+r"(peers)
+        : "r"(d), "n"(1 << BIT));
+    return peers;
+}
+__device__ __forceinline__ u32 match_digit_bits(u32 peers, u32 d) {
+    peers = match_digit_bit<0>(peers, d);
+    peers = match_digit_bit<1>(peers, d);
+    peers = match_digit_bit<2>(peers, d);
+    peers = match_digit_bit<3>(peers, d);
+    peers = match_digit_bit<4>(peers, d);
+    peers = match_digit_bit<5>(peers, d);
+    peers = match_digit_bit<6>(peers, d);
+    peers = match_digit_bit<7>(peers, d);
+    return peers;
+}
+
 // Digit selection.  ALIGNED (shift a multiple of 8, the only case the suffix sorter uses): the digit
 // is one byte of the high or low key word, a single PRMT.  Otherwise a generic 64-bit shift.
 template <bool ALIGNED>
@@ -133,16 +163,74 @@ struct DigitSel {
     }
 };
 
+// Batched decoupled look-back of one digit column: kBatch predecessor status words per L2 round trip.
+// issue() only starts the loads; consume() folds them (aggregates up to the nearest inclusive prefix)
+// and moves the cursor, so the round trip can be overlapped with other work.
+template <typename StatusT, int kBatch>
+struct DigitLookback {
+    typedef StatusTraits<StatusT> ST;
+    StatusT v[kBatch];
+    StatusT excl;
+    int t;
+    bool found, pending;
+    __device__ __forceinline__ void init(u32 tile) {
+        excl = 0;
+        t = (int)tile - 1;
+        found = tile == 0;
+        pending = false;
+    }
+    __device__ __forceinline__ void issue(const StatusT* __restrict__ status, int tid) {
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j)
+            v[j] = (t - j >= 0) ? ld_relaxed(status + (size_t)(t - j) * kRadix + tid) : ((StatusT)2 << ST::kShift);
+        pending = true;
+    }
+    __device__ __forceinline__ void consume() {
+        int used = kBatch;
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            if (j < used && !found) {
+                const u32 flag = (u32)(v[j] >> ST::kShift);
+                if (flag == 0) {
+                    used = j;  // not published yet: poll again from this tile
+                } else {
+                    excl += v[j] & ST::kMask;
+                    if (flag == 2) found = true;
+                }
+            }
+        }
+        t -= used;
+        pending = false;
+    }
+    // one overlapped step: fold what has arrived, start the next batch if still searching
+    __device__ __forceinline__ void step(const StatusT* __restrict__ status, int tid) {
+        if (found) return;
+        if (pending) consume();
+        if (!found) issue(status, tid);
+    }
+    __device__ __forceinline__ void finish(const StatusT* __restrict__ status, int tid) {
+        while (!found) {
+            if (!pending) issue(status, tid);
+            consume();
+        }
+    }
+};
+
 // The body of one tile.  FULL = all THREADS*ITEMS slots hold a pair (every tile but the last):
 // no validity predicates anywhere on that path.
-template <int THREADS, int ITEMS, typename StatusT, bool ALIGNED, bool FULL>
+// Tried and rejected (measurements in profiles/r1_pass_trace_v4.md): publishing the aggregate from a
+// shared-atomic pre-count and starting the look-back before the ranking loop (1.22-1.40 ms per 2^27
+// pairs instead of 1.07: the prefix still appears only after the ranking, so walks get longer), and a
+// dedicated scan warp doing the look-back beside the ranking warps (2.1 ms: one warp cannot keep enough
+// status loads in flight).
+template <int THREADS, int ITEMS, int ILP, typename StatusT, bool ALIGNED, bool FULL>
 __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, const u64* __restrict__ keys_in,
                                               const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
                                               u32* __restrict__ vals_out, const u32 tile, const u32 nvalid, const int shift,
                                               const u32* __restrict__ digit_base, StatusT* __restrict__ status,
                                               long long* __restrict__ trace) {
     // trace != nullptr (tools/pass_trace.py only): thread 0 stamps clock64() at the phase boundaries
-#define DARK_STAMP(i) do { if (trace && threadIdx.x == 0) trace[(size_t)tile * 8 + (i)] = clock64(); } while (0)
+#define DARK_STAMP(i) do { if (trace && threadIdx.x == 0) trace[(size_t)tile * 12 + (i)] = clock64(); } while (0)
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
     typedef StatusTraits<StatusT> ST;
     constexpr int TILE = Smem::kTile;
@@ -169,6 +257,11 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
+    constexpr int kLookbackBatch = 8;
+    DigitLookback<StatusT, kLookbackBatch> lb;
+    lb.init(tile);
+    u32 count = 0;
+
     // ---- rank inside the warp.  Lanes with equal digits are found with 8 ballots (one per digit bit;
     // match.any is microcoded per distinct value and was the top stall of the first version,
     // profiles/r1_ncu_c2_v1.md).  Every lane reads its digit's counter, the lowest lane of each group
@@ -181,16 +274,12 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
     for (int k = 0; k < ITEMS; ++k) {
         const bool valid = FULL || (local0 + k * 32) < nvalid;
         u32 d = digit(key[k]);
-        // Tie this item's ballots to the result of item k-2: without the false dependency the
-        // compiler hoists the votes of all ITEMS items to the top (150+ registers, one CTA per SM).
-        if (k >= 2) asm volatile("" : "+r"(d) : "r"(rank2[(k - 2) / 2]));
+        // Tie this item's ballots to the result of item k-ILP: without the false dependency the
+        // compiler hoists the votes of all ITEMS items to the top (150+ registers, one CTA per SM);
+        // ILP items stay in flight per warp.
+        if (k >= ILP) asm volatile("" : "+r"(d) : "r"(rank2[(k - ILP) / 2]));
         u32 peers = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
-#pragma unroll
-        for (int b = 0; b < kRadixBits; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const u32 vote = __ballot_sync(0xffffffffu, bit);
-            peers &= bit ? vote : ~vote;
-        }
+        peers = match_digit_bits(peers, d);
         const u32 prev = whist[d];  // every lane reads (padding lanes harmlessly), then the group's lowest lane bumps
         const u32 below = peers & lt;
         const u32 r = prev + __popc(below);
@@ -205,7 +294,6 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
     DARK_STAMP(3);
 
     // ---- per digit: exclusive offsets across warps, tile total, publish the aggregate
-    u32 count = 0;
     if (tid < kRadix) {
         u32 run = 0;
 #pragma unroll
@@ -251,40 +339,16 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
     }
 
     DARK_STAMP(5);
-    // ---- decoupled look-back over the predecessors' digit counts
+    // ---- decoupled look-back over the predecessors' digit counts.  Tiles finish every ~60 cycles
+    // chip-wide while a status read costs an L2 round trip (600+ cycles, more under load), so the
+    // nearest inclusive prefix is 10-25 tiles back: walking them one load at a time cost 34 % of the
+    // tile time (profiles/r1_pass_trace_v3.log); 8 predecessors are read per round trip.
     if (tid < kRadix) {
-        StatusT excl = 0;
         if (tile > 0) {
-            // Tiles finish every ~60 cycles chip-wide while one status read costs an L2 round trip
-            // (~600 cycles), so the nearest inclusive prefix is typically 10-15 tiles back: walking
-            // them one load at a time cost 34 % of the tile time (tools/pass_trace.py,
-            // profiles/r1_pass_trace_v3.log).  Read kLookbackBatch predecessors per round trip instead.
-            constexpr int kLookbackBatch = 8;
-            int t = (int)tile - 1;
-            bool found = false;
-            while (!found) {
-                StatusT v[kLookbackBatch];
-#pragma unroll
-                for (int j = 0; j < kLookbackBatch; ++j)
-                    v[j] = (t - j >= 0) ? ld_relaxed(status + (size_t)(t - j) * kRadix + tid) : ((StatusT)2 << ST::kShift);
-                int used = kLookbackBatch;
-#pragma unroll
-                for (int j = 0; j < kLookbackBatch; ++j) {
-                    if (j < used && !found) {
-                        const u32 flag = (u32)(v[j] >> ST::kShift);
-                        if (flag == 0) {
-                            used = j;  // not published yet: poll again from this tile
-                        } else {
-                            excl += v[j] & ST::kMask;
-                            if (flag == 2) found = true;
-                        }
-                    }
-                }
-                t -= used;
-            }
-            st_relaxed(status + (size_t)tile * kRadix + tid, ((StatusT)2 << ST::kShift) | (excl + count));
+            lb.finish(status, tid);
+            st_relaxed(status + (size_t)tile * kRadix + tid, ((StatusT)2 << ST::kShift) | (lb.excl + count));
         }
-        s.global_off[tid] = digit_base[tid] + (u32)excl - dstart;
+        s.global_off[tid] = digit_base[tid] + (u32)lb.excl - dstart;
     }
     __syncthreads();
     DARK_STAMP(6);
@@ -301,10 +365,15 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
         }
     }
     DARK_STAMP(7);
+    if (trace && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        trace[(size_t)tile * 12 + 10] = (long long)gt;
+    }
 #undef DARK_STAMP
 }
 
-template <int THREADS, int ITEMS, int MINBLOCKS, typename StatusT, bool ALIGNED>
+template <int THREADS, int ITEMS, int MINBLOCKS, int ILP, typename StatusT, bool ALIGNED>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
                 u32* __restrict__ vals_out, u32 m, int shift, const u32* __restrict__ digit_base,
@@ -312,30 +381,44 @@ k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in
     static_assert(THREADS >= kRadix && THREADS % 32 == 0, "one thread per digit is assumed");
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
     constexpr int TILE = Smem::kTile;
-    const long long t_entry = trace ? clock64() : 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x;
 
-    // Tile order.  The look-back only waits on lower-numbered tiles, so those must already be running.
-    // By default tiles are claimed from a counter in the order CTAs actually start (one L2 atomic
-    // round trip before the first load can be issued).  With tile_counter == nullptr the tile is
-    // blockIdx.x, relying on the hardware dispatching CTAs of a 1-D grid in index order.
-    if (tile_counter != nullptr && tid == 0) s.tile = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < Smem::kWarps * kRadix; i += THREADS) (&s.warp_hist[0][0])[i] = 0;
-    __syncthreads();
-    const u32 tile = tile_counter != nullptr ? s.tile : blockIdx.x;
-    if (trace && tid == 0) {
-        trace[(size_t)tile * 8 + 0] = t_entry;
-        trace[(size_t)tile * 8 + 1] = clock64();
+    // Persistent CTAs: the grid is (SMs x resident CTAs) and every CTA claims tiles from a counter until
+    // none are left.  Tiles are thereby numbered in the order they are started, so the look-back only
+    // ever waits on tiles that are already running; and a CTA no longer has to drain its scattered
+    // stores and be re-launched between tiles — with one tile per CTA the SMs held only 1.8 of 3
+    // resident tiles on average (tools/pass_trace.py, profiles/r1_pass_trace_v4.log).
+    // tile_counter == nullptr (test knob) falls back to one tile per CTA numbered by blockIdx.x.
+    const u32 num_tiles = (u32)(((u64)m + TILE - 1) / TILE);
+    for (;;) {
+        const long long t_claim = trace ? clock64() : 0;
+        if (tile_counter != nullptr && tid == 0) s.tile = atomicAdd(tile_counter, 1u);
+        for (int i = tid; i < Smem::kWarps * kRadix; i += THREADS) (&s.warp_hist[0][0])[i] = 0;
+        __syncthreads();
+        const u32 tile = tile_counter != nullptr ? s.tile : blockIdx.x;
+        if (tile >= num_tiles) break;
+        if (trace && tid == 0) {
+            trace[(size_t)tile * 12 + 0] = t_claim;
+            trace[(size_t)tile * 12 + 1] = clock64();
+            unsigned long long gt;
+            unsigned int smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            trace[(size_t)tile * 12 + 8] = (long long)gt;
+            trace[(size_t)tile * 12 + 9] = (long long)smid;
+        }
+        const u32 nvalid = (u32)min((u64)TILE, (u64)m - (u64)tile * TILE);
+        if (nvalid == TILE)
+            onesweep_tile<THREADS, ITEMS, ILP, StatusT, ALIGNED, true>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid,
+                                                                              shift, digit_base, status, trace);
+        else
+            onesweep_tile<THREADS, ITEMS, ILP, StatusT, ALIGNED, false>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid,
+                                                                               shift, digit_base, status, trace);
+        if (tile_counter == nullptr) break;
+        __syncthreads();  // the scatter has read the shared tile: it may be overwritten now
     }
-    const u32 nvalid = (u32)min((u64)TILE, (u64)m - (u64)tile * TILE);
-    if (nvalid == TILE)
-        onesweep_tile<THREADS, ITEMS, StatusT, ALIGNED, true>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid, shift,
-                                                              digit_base, status, trace);
-    else
-        onesweep_tile<THREADS, ITEMS, StatusT, ALIGNED, false>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid, shift,
-                                                               digit_base, status, trace);
 }
 
 }  // namespace dark

@@ -164,7 +164,7 @@ FORCED_PATHS = [
     ({"DARK_BWT_EMIT_WINDOW_MB": "1"}, "mixed", 7, 5000011),         # windowed BWT emission (text larger than L2)
     ({"DARK_BWT_EMIT_WINDOW_MB": "1", "DARK_BWT_BUCKETED": "1"}, "text", 3, 2500000),
     ({"DARK_BWT_SORT_VARIANT": "0"}, "mixed", 4, 700001),            # the other radix-pass tilings
-    ({"DARK_BWT_SORT_VARIANT": "3"}, "mixed", 4, 700001),
+    ({"DARK_BWT_SORT_VARIANT": "2"}, "mixed", 4, 700001),
     ({"DARK_BWT_SORT_VARIANT": "5"}, "dna", 1, 700001),
     ({"DARK_BWT_TILE_BY_BLOCKIDX": "1"}, "mixed", 9, 900001),        # tiles ordered by blockIdx instead of the claim counter
 ]
