@@ -433,7 +433,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
 
     // ---- round 0: keys of K symbols, ids descending
     {
-        const u32 blocks = (u32)ceil_div(n, kInitThreads * kInitItems);
+        const u32 blocks = (u32)std::min<u64>(ceil_div(n, kInitThreads * kInitItems), (u64)ctx->num_sms * 8);
 #define INIT_PACKED(S)                                                                                            \
     k_init_keys_packed<kInitThreads, kInitItems, S><<<blocks, kInitThreads, 0, ctx->stream>>>(d_text, n, ctx->lut, \
                                                                                               ctx->keys[0], ctx->ids[0], ctx->hist)
@@ -537,7 +537,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         }
         CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
         {
-            const u32 blocks = (u32)ceil_div(m, kBuildThreads * kBuildItems);
+            const u32 blocks = (u32)ceil_div(m, kBuildThreads * kBuildItems);  // one tile per CTA: the gathers want every warp slot filled
             k_build_keys<kBuildThreads, kBuildItems><<<blocks, kBuildThreads, 0, ctx->stream>>>(
                 ctx->ids[cur], ctx->ranks, m, n, h, kb, ctx->isa, ctx->keys[cur], ctx->hist, passes_r);
             LAUNCHED();

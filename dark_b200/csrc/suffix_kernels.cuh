@@ -85,29 +85,34 @@ k_init_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ lut, int 
     for (int i = tid; i < 256; i += THREADS) s_lut[i] = lut[i];
     __syncthreads();
 
-    const u64 jb = (u64)blockIdx.x * TILE;
-    const u32 cnt = (u32)min((u64)TILE, (u64)n - jb);
-    const u64 i_lo = (u64)n - jb - cnt;  // lowest text position of this tile
-    const u32 span = cnt + K - 1;
-    for (u32 x = tid; x < span; x += THREADS) {
-        const u64 pos = i_lo + x;
-        s_code[x] = pos < n ? s_lut[text[pos]] : (u8)0;
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int k = 0; k < ITEMS; ++k) {
-        const u32 jl = k * THREADS + tid;
-        if (jl < cnt) {
-            const u32 x = cnt - 1 - jl;  // position i = i_lo + x
-            u64 key = 0;
-            for (int c = 0; c < K; ++c) key = (key << s_bits) | s_code[x + c];
-            key <<= (64 - s_bits * K);  // symbol field MSB-aligned, so "the top 8t bits" are whole leading symbols
-            keys_out[jb + jl] = key;
-            ids_out[jb + jl] = (u32)(i_lo + x);
-            hist_add_key(s_hist, key, 0, num_passes);
+    // a capped grid loops over the tiles, so the shared histogram is flushed (2,048 global atomics)
+    // once per CTA instead of once per tile — the flush was a third of this kernel's stalls
+    const u32 ntiles = (u32)(((u64)n + TILE - 1) / TILE);
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const u64 jb = (u64)tile * TILE;
+        const u32 cnt = (u32)min((u64)TILE, (u64)n - jb);
+        const u64 i_lo = (u64)n - jb - cnt;  // lowest text position of this tile
+        const u32 span = cnt + K - 1;
+        for (u32 x = tid; x < span; x += THREADS) {
+            const u64 pos = i_lo + x;
+            s_code[x] = pos < n ? s_lut[text[pos]] : (u8)0;
         }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < ITEMS; ++k) {
+            const u32 jl = k * THREADS + tid;
+            if (jl < cnt) {
+                const u32 x = cnt - 1 - jl;  // position i = i_lo + x
+                u64 key = 0;
+                for (int c = 0; c < K; ++c) key = (key << s_bits) | s_code[x + c];
+                key <<= (64 - s_bits * K);  // symbol field MSB-aligned, so "the top 8t bits" are whole leading symbols
+                keys_out[jb + jl] = key;
+                ids_out[jb + jl] = (u32)(i_lo + x);
+                hist_add_key(s_hist, key, 0, num_passes);
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     hist_flush(s_hist, g_hist, num_passes, tid, THREADS);
 }
 
@@ -131,38 +136,41 @@ k_init_keys_packed(const u8* __restrict__ text, u32 n, const u8* __restrict__ lu
     for (int i = tid; i < 256; i += THREADS) s_lut[i] = lut[i];
     __syncthreads();
 
-    const u64 jb = (u64)blockIdx.x * TILE;
-    const u32 cnt = (u32)min((u64)TILE, (u64)n - jb);
-    const u64 i_lo = (u64)n - jb - cnt;
-    for (int w = tid; w < NWORDS; w += THREADS) {
-        u32 word = 0;
-        const u64 pos0 = i_lo + (u64)w * SPW;
+    const u32 ntiles = (u32)(((u64)n + TILE - 1) / TILE);
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // capped grid: one histogram flush per CTA
+        const u64 jb = (u64)tile * TILE;
+        const u32 cnt = (u32)min((u64)TILE, (u64)n - jb);
+        const u64 i_lo = (u64)n - jb - cnt;
+        for (int w = tid; w < NWORDS; w += THREADS) {
+            u32 word = 0;
+            const u64 pos0 = i_lo + (u64)w * SPW;
 #pragma unroll
-        for (int c = 0; c < SPW; ++c) {
-            const u64 pos = pos0 + c;
-            const u32 code = pos < n ? (u32)s_lut[text[pos]] : 0u;
-            word = (S == 32 ? 0u : (word << (S & 31))) | code;
+            for (int c = 0; c < SPW; ++c) {
+                const u64 pos = pos0 + c;
+                const u32 code = pos < n ? (u32)s_lut[text[pos]] : 0u;
+                word = (S == 32 ? 0u : (word << (S & 31))) | code;
+            }
+            s_words[w] = word;
         }
-        s_words[w] = word;
-    }
-    __syncthreads();
+        __syncthreads();
 #pragma unroll 4
-    for (int k = 0; k < ITEMS; ++k) {
-        const u32 jl = k * THREADS + tid;
-        if (jl < cnt) {
-            const u32 x = cnt - 1 - jl;
-            const u32 bit = x * S;
-            const u32 wi = bit >> 5, sh = bit & 31;
-            const u32 w0 = s_words[wi], w1 = s_words[wi + 1], w2 = s_words[wi + 2];
-            const u32 hi = __funnelshift_l(w1, w0, sh);
-            const u32 lo = __funnelshift_l(w2, w1, sh);
-            const u64 key = ((u64)hi << 32) | lo;
-            keys_out[jb + jl] = key;
-            ids_out[jb + jl] = (u32)(i_lo + x);
-            hist_add_key(s_hist, key, 0, kMaxPasses);
+        for (int k = 0; k < ITEMS; ++k) {
+            const u32 jl = k * THREADS + tid;
+            if (jl < cnt) {
+                const u32 x = cnt - 1 - jl;
+                const u32 bit = x * S;
+                const u32 wi = bit >> 5, sh = bit & 31;
+                const u32 w0 = s_words[wi], w1 = s_words[wi + 1], w2 = s_words[wi + 2];
+                const u32 hi = __funnelshift_l(w1, w0, sh);
+                const u32 lo = __funnelshift_l(w2, w1, sh);
+                const u64 key = ((u64)hi << 32) | lo;
+                keys_out[jb + jl] = key;
+                ids_out[jb + jl] = (u32)(i_lo + x);
+                hist_add_key(s_hist, key, 0, kMaxPasses);
+            }
         }
+        __syncthreads();
     }
-    __syncthreads();
     hist_flush(s_hist, g_hist, kMaxPasses, tid, THREADS);
 }
 
@@ -177,26 +185,29 @@ k_build_keys(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m, 
     const int tid = threadIdx.x;
     hist_clear(s_hist, tid, THREADS);
     __syncthreads();
-    const u64 base = (u64)blockIdx.x * (THREADS * ITEMS);
-    u32 id[ITEMS], r2[ITEMS];
+    const u32 ntiles = (u32)(((u64)m + THREADS * ITEMS - 1) / (THREADS * ITEMS));
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // capped grid: one histogram flush per CTA
+        const u64 base = (u64)tile * (THREADS * ITEMS);
+        u32 id[ITEMS], r2[ITEMS];
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const u64 p = base + k * THREADS + tid;
-        id[k] = p < m ? ld_stream(ids + p) : 0u;
-    }
+        for (int k = 0; k < ITEMS; ++k) {
+            const u64 p = base + k * THREADS + tid;
+            id[k] = p < m ? ld_stream(ids + p) : 0u;
+        }
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const u64 p = base + k * THREADS + tid;
-        const u64 pos2 = (u64)id[k] + h;
-        r2[k] = (p < m && pos2 < n) ? __ldg(isa + pos2) + 1u : 0u;
-    }
+        for (int k = 0; k < ITEMS; ++k) {
+            const u64 p = base + k * THREADS + tid;
+            const u64 pos2 = (u64)id[k] + h;
+            r2[k] = (p < m && pos2 < n) ? __ldg(isa + pos2) + 1u : 0u;
+        }
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const u64 p = base + k * THREADS + tid;
-        if (p < m) {
-            const u64 key = ((u64)ld_stream(ranks + p) << kb) | r2[k];
-            keys_out[p] = key;
-            hist_add_key(s_hist, key, 0, num_passes);
+        for (int k = 0; k < ITEMS; ++k) {
+            const u64 p = base + k * THREADS + tid;
+            if (p < m) {
+                const u64 key = ((u64)ld_stream(ranks + p) << kb) | r2[k];
+                keys_out[p] = key;
+                hist_add_key(s_hist, key, 0, num_passes);
+            }
         }
     }
     __syncthreads();
