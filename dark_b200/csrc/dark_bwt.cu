@@ -172,7 +172,7 @@ int next_counter(dark_bwt_ctx* ctx, u32** out) {
 // chosen from measurements (profiles/); DARK_BWT_SORT_VARIANT=<i> selects another one for sweeps.
 template <int THREADS, int ITEMS, int MINBLOCKS, int ILP, typename StatusT, bool ALIGNED>
 int launch_pass_kernel(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
-                       const u32* digit_base, u32* counter, u32 tiles) {
+                       const u32* digit_base, u32* counter, u32 tiles, const u8* prev_text, u32 n_text) {
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
     auto kern = k_onesweep_pass<THREADS, ITEMS, MINBLOCKS, ILP, StatusT, ALIGNED>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));  // per device
@@ -180,21 +180,21 @@ int launch_pass_kernel(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* k
     // persistent grid: as many CTAs as stay resident (SMs x MINBLOCKS), each claiming tiles until none are left
     const u32 grid = by_block_index ? tiles : std::min<u32>(tiles, (u32)ctx->num_sms * MINBLOCKS);
     kern<<<grid, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base, (StatusT*)ctx->sort_status,
-                                                        by_block_index ? nullptr : counter, ctx->pass_trace);
+                                                        by_block_index ? nullptr : counter, ctx->pass_trace, prev_text, n_text);
     LAUNCHED();
     return 0;
 }
 
 template <int THREADS, int ITEMS, int MINBLOCKS, int ILP>
 int launch_pass_variant(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
-                        const u32* digit_base, u32* counter, bool wide) {
+                        const u32* digit_base, u32* counter, bool wide, const u8* prev_text, u32 n_text) {
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
     const u32 tiles = (u32)ceil_div(m, Smem::kTile);
     const size_t bytes = (size_t)tiles * kRadix * (wide ? sizeof(u64) : sizeof(u32));
     if (bytes > ctx->sort_status_bytes) return ctx->fail_internal("sort status buffer too small");
     CK(cudaMemsetAsync(ctx->sort_status, 0, bytes, ctx->stream));
     const bool aligned = (shift & 7) == 0;  // always true for the suffix sorter; the public sort may differ
-#define LP(ST, AL) launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, ILP, ST, AL>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, tiles)
+#define LP(ST, AL) launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, ILP, ST, AL>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, tiles, prev_text, n_text)
     if (!aligned) return wide ? LP(u64, false) : LP(u32, false);
     return wide ? LP(u64, true) : LP(u32, true);
 #undef LP
@@ -204,7 +204,7 @@ constexpr int kDefaultSortVariant = 1;  // 256 threads x 16 items, 3 CTAs/SM: be
 
 // One onesweep pass over m pairs: buffers[cur] -> buffers[cur^1].
 int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
-                const u32* digit_base) {
+                const u32* digit_base, const u8* prev_text = nullptr, u32 n_text = 0) {
     u32* counter = nullptr;
     if (int rc = next_counter(ctx, &counter)) return rc;
     // 32-bit status words hold prefixes below 2^30; larger sorts (2 GiB blocks) use 64-bit words.
@@ -212,7 +212,7 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
     const bool wide = !(m < (1u << 30)) || getenv("DARK_BWT_FORCE_U64_STATUS") != nullptr;
     const char* ev = getenv("DARK_BWT_SORT_VARIANT");
     const int variant = ev ? atoi(ev) : kDefaultSortVariant;
-#define V(T, I, B, L) return launch_pass_variant<T, I, B, L>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide)
+#define V(T, I, B, L) return launch_pass_variant<T, I, B, L>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, n_text)
     switch (variant) {
         case 0: V(256, 16, 2, 2);
         case 2: V(256, 12, 3, 2);
@@ -235,7 +235,8 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
 // block tied; measured: C2 8 -> 5 passes + one 65,792-element round; C1/C5 unchanged.
 // *first_pass_out = index of the lowest digit that was sorted.
 int run_sort(dark_bwt_ctx* ctx, u64* const keys[2], u32* const vals[2], int cur, u32 m, int begin_bit, int num_passes,
-             int* cur_out, dark_bwt_stats* st, int round, bool prune = false, int* first_pass_out = nullptr) {
+             int* cur_out, dark_bwt_stats* st, int round, bool prune = false, int* first_pass_out = nullptr,
+             const u8* patch_text = nullptr, bool* patched_out = nullptr) {
     // Scalar results (flags, counts, origin) are written by the kernels directly into mapped pinned host
     // memory and read after a stream sync.  A cudaMemcpy D2H would queue on the copy engine behind the
     // 256 MB block transfers of the pipelined batch entry (measured: +5 ms per block).
@@ -259,12 +260,18 @@ int run_sort(dark_bwt_ctx* ctx, u64* const keys[2], u32* const vals[2], int cur,
         if (first < 0) first = 0;
     }
     if (first_pass_out) *first_pass_out = first;
+    // pruned by at least one digit: the first pass that runs also drops the BWT byte into the low key byte
+    const u8* patch = (first >= 1) ? patch_text : nullptr;
     const int sp = span_begin(ctx, PH_PASS);
     for (int p = first; p < num_passes; ++p) {
         if (ctx->mail->trivial[p]) continue;  // every key has the same digit: the pass is the identity
         if (int rc = launch_pass(ctx, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], m, begin_bit + p * kRadixBits,
-                                 ctx->hist + p * kRadix))
+                                 ctx->hist + p * kRadix, patch, m))
             return rc;
+        if (patch) {
+            if (patched_out) *patched_out = true;
+            patch = nullptr;
+        }
         cur ^= 1;
         if (st) {
             st->sort_passes += 1;
@@ -285,7 +292,7 @@ struct PairSink {  // where a PAIRS re-rank puts its (id, rank) updates
 
 template <bool ROUND0, bool PAIRS>
 int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32 n, int K, int kb, u32* sa, u32* out_ids,
-                  PairSink sink = PairSink()) {
+                  const u8* text, u8* bwt_inline, PairSink sink = PairSink()) {
     const u32 tiles = (u32)ceil_div(m, kScanTile);
     if (tiles > ctx->scan_tiles) return ctx->fail_internal("scan tile state too small");
     u32* counter = nullptr;
@@ -294,7 +301,7 @@ int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32
     ScanTileState ts{ctx->scan_words};
     k_rerank<kScanThreads, kScanItems, ROUND0, PAIRS><<<tiles, kScanThreads, 0, ctx->stream>>>(
         keys, ids, m, n, K, kb, ctx->isa, sa, out_ids, ctx->ranks, ts, counter, &ctx->mail_dev->count, sink.ids, sink.vals,
-        ctx->bucket_hist, sink.shift);
+        ctx->bucket_hist, sink.shift, text, bwt_inline, &ctx->mail_dev->origin);
     LAUNCHED();
     return 0;
 }
@@ -454,8 +461,16 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     int cur = 0;
     int first_pass = 0;
     sp = span_begin(ctx, PH_SORT);
-    if (int rc = run_sort(ctx, ctx->keys, ctx->ids, cur, n, 0, passes0, &cur, st, 0, /*prune=*/!no_pack, &first_pass)) return rc;
+    // Inline emission: when the initial sort is pruned by >= 1 digit the BWT byte of each suffix travels in
+    // the (unsorted) low key byte and is emitted as the suffix settles; no gather pass at the end.
+    const char* iev = getenv("DARK_BWT_INLINE_EMIT");
+    const bool want_inline = iev ? atoi(iev) != 0 : true;
+    bool emit_inline = false;
+    if (int rc = run_sort(ctx, ctx->keys, ctx->ids, cur, n, 0, passes0, &cur, st, 0, /*prune=*/!no_pack, &first_pass,
+                          want_inline ? d_text : nullptr, &emit_inline))
+        return rc;
     span_end(ctx, sp);
+    u8* bwt_inline = emit_inline ? d_bwt : nullptr;
     // The sort covered the key bits above `drop`: K0 whole leading symbols are known equal inside a
     // tie group, Kc symbols were touched (a suffix shorter than Kc had padding compared).
     const int drop = first_pass * kRadixBits;
@@ -470,7 +485,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     const int passes_r = (key_bits + kRadixBits - 1) / kRadixBits;
 
     sp = span_begin(ctx, PH_RERANK);
-    if (int rc = launch_rerank<true, false>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, Kc, drop, sa, ctx->ids[cur ^ 1])) return rc;
+    if (int rc = launch_rerank<true, false>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, Kc, drop, sa, ctx->ids[cur ^ 1], d_text, bwt_inline)) return rc;
     span_end(ctx, sp);
     cur ^= 1;  // the compacted active ids now live in ids[cur]
     u32 m = 0;
@@ -556,14 +571,14 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
             sink.vals = sink.ids + ma;
             sink.shift = bshift;
             CK(cudaMemsetAsync(ctx->bucket_hist, 0, sizeof(u32) * 256, ctx->stream));
-            if (int rc = launch_rerank<false, true>(ctx, ctx->keys[cur], ctx->ids[cur], m, n, K, kb, sa, ctx->ids[cur ^ 1], sink)) return rc;
+            if (int rc = launch_rerank<false, true>(ctx, ctx->keys[cur], ctx->ids[cur], m, n, K, kb, sa, ctx->ids[cur ^ 1], d_text, bwt_inline, sink)) return rc;
             if (int rc = bucket_scan(ctx)) return rc;
             u32* oi = (u32*)ctx->keys[cur];  // the sorted keys are dead once the re-rank has run
             u32* ov = oi + ma;
             if (int rc = bucket_partition(ctx, sink.ids, sink.vals, m, bshift, oi, ov)) return rc;
             if (int rc = bucket_scatter(ctx, oi, ov, m)) return rc;
         } else {
-            if (int rc = launch_rerank<false, false>(ctx, ctx->keys[cur], ctx->ids[cur], m, n, K, kb, sa, ctx->ids[cur ^ 1])) return rc;
+            if (int rc = launch_rerank<false, false>(ctx, ctx->keys[cur], ctx->ids[cur], m, n, K, kb, sa, ctx->ids[cur ^ 1], d_text, bwt_inline)) return rc;
         }
         span_end(ctx, sp);
         cur ^= 1;
@@ -574,7 +589,8 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
 
     // ---- BWT bytes + origin
     sp = span_begin(ctx, PH_EMIT);
-    if (int rc = emit(ctx, d_text, n, sa, d_bwt)) return rc;
+    if (!emit_inline)
+        if (int rc = emit(ctx, d_text, n, sa, d_bwt)) return rc;
     span_end(ctx, sp);
     const int e_last = ctx->n_events++;
     CK(cudaEventRecord(ctx->events[e_last], ctx->stream));

@@ -228,7 +228,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
                                               const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
                                               u32* __restrict__ vals_out, const u32 tile, const u32 nvalid, const int shift,
                                               const u32* __restrict__ digit_base, StatusT* __restrict__ status,
-                                              long long* __restrict__ trace) {
+                                              long long* __restrict__ trace, const u8* __restrict__ prev_text, const u32 n_text) {
     // trace != nullptr (tools/pass_trace.py only): thread 0 stamps clock64() at the phase boundaries
 #define DARK_STAMP(i) do { if (trace && threadIdx.x == 0) trace[(size_t)tile * 12 + (i)] = clock64(); } while (0)
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
@@ -245,6 +245,19 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
     u64 key[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) key[k] = (FULL || local0 + k * 32 < nvalid) ? ld_stream(kp + k * 32) : ~0ull;
+    if (prev_text != nullptr) {
+        // First pass of a pruned initial sort (the low key byte is not sorted): element j is still suffix
+        // n-1-j, so its BWT byte T[id-1] is a contiguous read; it rides in the low key byte from here on
+        // and the round-0 re-rank emits it for every suffix it settles — no gather for those.
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const u64 j = tile_base + local0 + k * 32;
+            if (FULL || local0 + k * 32 < nvalid) {
+                const u32 id = n_text - 1 - (u32)j;
+                key[k] = (key[k] & ~0xFFull) | (u64)__ldg(prev_text + (id == 0 ? n_text - 1 : id - 1));
+            }
+        }
+    }
     // The values go straight to shared memory with cp.async (no registers held across the ranking
     // loop, latency hidden behind it); each thread later reads back exactly the words it copied.
     {
@@ -377,7 +390,8 @@ template <int THREADS, int ITEMS, int MINBLOCKS, int ILP, typename StatusT, bool
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
                 u32* __restrict__ vals_out, u32 m, int shift, const u32* __restrict__ digit_base,
-                StatusT* __restrict__ status, u32* __restrict__ tile_counter, long long* __restrict__ trace) {
+                StatusT* __restrict__ status, u32* __restrict__ tile_counter, long long* __restrict__ trace,
+                const u8* __restrict__ prev_text, u32 n_text) {
     static_assert(THREADS >= kRadix && THREADS % 32 == 0, "one thread per digit is assumed");
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
     constexpr int TILE = Smem::kTile;
@@ -412,10 +426,10 @@ k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in
         const u32 nvalid = (u32)min((u64)TILE, (u64)m - (u64)tile * TILE);
         if (nvalid == TILE)
             onesweep_tile<THREADS, ITEMS, ILP, StatusT, ALIGNED, true>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid,
-                                                                              shift, digit_base, status, trace);
+                                                                              shift, digit_base, status, trace, prev_text, n_text);
         else
             onesweep_tile<THREADS, ITEMS, ILP, StatusT, ALIGNED, false>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid,
-                                                                               shift, digit_base, status, trace);
+                                                                               shift, digit_base, status, trace, prev_text, n_text);
         if (tile_counter == nullptr) break;
         __syncthreads();  // the scatter has read the shared tile: it may be overwritten now
     }

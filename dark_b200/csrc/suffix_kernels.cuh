@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(THREADS, 2)
 k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n, int K, int kb, u32* __restrict__ isa,
          u32* __restrict__ sa, u32* __restrict__ out_ids, u32* __restrict__ out_ranks, ScanTileState ts,
          u32* __restrict__ tile_counter, u32* __restrict__ out_count, u32* __restrict__ pair_ids,
-         u32* __restrict__ pair_vals, u32* __restrict__ pair_hist, int pair_shift) {
+         u32* __restrict__ pair_vals, u32* __restrict__ pair_hist, int pair_shift, const u8* __restrict__ text,
+         u8* __restrict__ bwt_inline, u64* __restrict__ origin) {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
     __shared__ ScanTriple s_warp[WARPS];
@@ -453,7 +454,10 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
     // (per-lane 4-byte stores at a 32 B stride cost one L2 sector operation each; the first version
     // spent its time there: 3 sector writes per element, profiles/r1_ncu_c5_c3_v2.md).
     const u32 tile_cnt0 = s_excl.cnt;  // survivors before this tile
+    // bwt_inline != nullptr: BWT bytes are emitted as suffixes settle.  In round 0 the byte T[id-1] sits
+    // in the low key byte (pruned initial sort, see the radix pass); later rounds gather it.
     u32 v_sa[ITEMS], v_pid[ITEMS], v_pval[ITEMS];
+    u32 v_b0 = 0, v_b1 = 0;  // round 0: the 8 BWT bytes of this thread's slots
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const u64 p = p0 + k;
@@ -481,6 +485,17 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
                 isa[sid] = r_new;
             }
             if (ROUND0 && single) v_sa[k] = sid;
+            if (bwt_inline != nullptr && single) {
+                if (ROUND0) {
+                    const u32 byte = (u32)key[k + 1] & 0xFFu;
+                    if (k < 4) v_b0 |= byte << (8 * k);
+                    else v_b1 |= byte << (8 * (k - 4));
+                    if (sid == 0) *origin = p;
+                } else {
+                    bwt_inline[r_new] = __ldg(text + (sid == 0 ? n - 1 : sid - 1));
+                    if (sid == 0) *origin = r_new;
+                }
+            }
             if (single) {
                 if (!ROUND0) sa[r_new] = sid;
             } else {
@@ -501,6 +516,15 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k)
                 if (p0 + k < m) sa[p0 + k] = v_sa[k];
+        }
+    }
+    if (ROUND0 && bwt_inline != nullptr) {  // unsettled slots get a placeholder now and their byte when they settle
+        if (p0 + ITEMS <= m && (((uintptr_t)bwt_inline) & 7) == 0) {
+            *reinterpret_cast<uint2*>(bwt_inline + p0) = make_uint2(v_b0, v_b1);
+        } else {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k)
+                if (p0 + k < m) bwt_inline[p0 + k] = (u8)((k < 4 ? v_b0 >> (8 * k) : v_b1 >> (8 * (k - 4))) & 0xFFu);
         }
     }
     if (PAIRS) {
