@@ -495,6 +495,8 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     // survive; otherwise only the survivors' now, and per round the few that are actually read.
     bool isa_complete = true;
     int selective_rounds = 0;
+    const char* sev = getenv("DARK_BWT_RANK_SEARCH");
+    const bool use_search = sev ? atoi(sev) != 0 : true;
     // Scatters of more than n/16 ranks into an isa[] that outgrows L2 go through the bucketed path.
     const char* bev = getenv("DARK_BWT_BUCKETED");
     const bool bucketed = bev ? atoi(bev) != 0 : ((u64)n * 4 > (96ull << 20));
@@ -534,9 +536,18 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
             st->rounds = round;
         }
         sp = span_begin(ctx, PH_KEYBUILD);
+        CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
+        bool keys_built = false;
         if (!isa_complete) {
             // ranks of suffixes settled in round 0 exist only where they are about to be read
-            if (selective_rounds < 2) {
+            if (round == 1 && use_search) {
+                // round 1: read the ranks off the sorted round-0 keys (still intact in keys[cur^1] / ids[cur^1])
+                k_build_keys_search<256><<<(u32)ceil_div(m, 256), 256, 0, ctx->stream>>>(
+                    ctx->ids[cur], ctx->ranks, m, n, h, kb, ctx->keys[cur ^ 1], ctx->ids[cur ^ 1], d_text, ctx->lut, s_bits, K, Kc,
+                    drop, ctx->keys[cur], ctx->hist, passes_r);
+                LAUNCHED();
+                keys_built = true;
+            } else if (selective_rounds < 2) {
                 const size_t words = (size_t)ceil_div(n, 32);
                 CK(cudaMemsetAsync(ctx->bitmap, 0, words * sizeof(u32), ctx->stream));
                 k_mark_needed<256><<<(u32)ceil_div(m, 256), 256, 0, ctx->stream>>>(ctx->ids[cur], m, n, h, ctx->bitmap);
@@ -550,8 +561,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
                 isa_complete = true;
             }
         }
-        CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
-        {
+        if (!keys_built) {
             const u32 blocks = (u32)ceil_div(m, kBuildThreads * kBuildItems);  // one tile per CTA: the gathers want every warp slot filled
             k_build_keys<kBuildThreads, kBuildItems><<<blocks, kBuildThreads, 0, ctx->stream>>>(
                 ctx->ids[cur], ctx->ranks, m, n, h, kb, ctx->isa, ctx->keys[cur], ctx->hist, passes_r);

@@ -214,6 +214,59 @@ k_build_keys(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m, 
     hist_flush(s_hist, g_hist, num_passes, tid, THREADS);
 }
 
+// Round 1 after a pruned round 0 with few survivors: no rank array exists yet (round 0 scatters none), and
+// filling even the needed part of it means a pass over the whole suffix array.  The rank of suffix
+// j = i+h after round 0 is the slot of the head of its tie group, which can be read off the SORTED
+// round-0 keys directly: lower bound of j's key prefix, then past the (at most Kc-1) short suffixes that
+// tie with it.  ~log2(n) dependent reads per survivor instead of a 4n-byte sweep.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_build_keys_search(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m, u32 n, u64 h, int kb,
+                    const u64* __restrict__ sorted_keys, const u32* __restrict__ sorted_ids, const u8* __restrict__ text,
+                    const u8* __restrict__ lut, int s_bits, int K, int Kc, int drop, u64* __restrict__ keys_out,
+                    u32* __restrict__ g_hist, int num_passes) {
+    __shared__ u32 s_hist[kMaxPasses * kRadix];
+    __shared__ u8 s_lut[256];
+    const int tid = threadIdx.x;
+    hist_clear(s_hist, tid, THREADS);
+    for (int i = tid; i < 256; i += THREADS) s_lut[i] = lut[i];
+    __syncthreads();
+    const u64 p = (u64)blockIdx.x * THREADS + tid;
+    if (p < m) {
+        const u64 j = (u64)ids[p] + h;
+        u32 r2 = 0;
+        if (j < n) {
+            // key prefix of suffix j exactly as the initial key builder packs it (MSB-aligned, zero padded)
+            u64 kj = 0;
+            for (int c = 0; c < K; ++c) {
+                const u64 pos = j + c;
+                kj = (kj << s_bits) | (pos < n && c < Kc ? (u64)s_lut[text[pos]] : 0ull);
+            }
+            kj <<= (64 - s_bits * K);
+            const u64 want = kj >> drop;
+            u32 lo = 0, hi = n;  // first slot whose sorted prefix is >= want
+            while (lo < hi) {
+                const u32 mid = lo + ((hi - lo) >> 1);
+                if ((sorted_keys[mid] >> drop) < want) lo = mid + 1;
+                else hi = mid;
+            }
+            const u64 short_from = (u64)n >= (u64)Kc ? (u64)n - Kc + 1 : 0;
+            u32 slot = lo;
+            if (j >= short_from) {
+                while (slot < n && sorted_ids[slot] != (u32)j) ++slot;          // a short suffix is its own group
+            } else {
+                while (slot < n && (sorted_keys[slot] >> drop) == want && sorted_ids[slot] >= short_from) ++slot;  // skip tied shorts
+            }
+            r2 = slot + 1;
+        }
+        const u64 key = ((u64)ranks[p] << kb) | r2;
+        keys_out[p] = key;
+        hist_add_key(s_hist, key, 0, num_passes);
+    }
+    __syncthreads();
+    hist_flush(s_hist, g_hist, num_passes, tid, THREADS);
+}
+
 // ---- re-rank + compaction: one decoupled look-back scan ------------------------------------------
 // Input: the active list sorted by key.  A "new head" starts a run of equal keys (= a group of
 // suffixes still tied after 2h symbols); an "old head" starts a run of equal key>>kb (the group the

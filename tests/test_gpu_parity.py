@@ -167,6 +167,7 @@ FORCED_PATHS = [
     ({"DARK_BWT_SORT_VARIANT": "2"}, "mixed", 4, 700001),
     ({"DARK_BWT_SORT_VARIANT": "5"}, "dna", 1, 700001),
     ({"DARK_BWT_TILE_BY_BLOCKIDX": "1"}, "mixed", 9, 900001),
+    ({"DARK_BWT_RANK_SEARCH": "0"}, "dna", 6, 1500003),              # selective rank fill (bitmap + SA sweep) instead of the search
     ({"DARK_BWT_INLINE_EMIT": "0"}, "dna", 3, 1200007),              # pruned initial sort WITHOUT inline emission
     ({"DARK_BWT_INLINE_EMIT": "0", "DARK_BWT_EMIT_WINDOW_MB": "1"}, "dna", 4, 3000001),        # tiles ordered by blockIdx instead of the claim counter
 ]
