@@ -610,6 +610,65 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     return DARK_BWT_OK;
 }
 
+// Inverse BWT on device buffers (kernels and method: suffix_kernels.cuh, "inverse BWT").
+int inverse_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, u64 origin64, u8* d_text, float* ms_out) {
+    if (n64 < 1 || n64 > ctx->capacity || n64 > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;
+    if (origin64 >= n64) return DARK_BWT_E_INVALID_ARG;
+    const u32 n = (u32)n64, origin = (u32)origin64;
+    CK(cudaSetDevice(ctx->device));
+    ctx->n_events = 0;
+    ctx->spans.clear();
+    ctx->next_counter = 0;
+    cudaEvent_t ea = ctx->events[kMaxEvents - 1], eb = ctx->events[kMaxEvents - 2];
+    CK(cudaEventRecord(ea, ctx->stream));
+    CK(cudaMemsetAsync(ctx->counters, 0, sizeof(u32) * kMaxCounters, ctx->stream));
+    CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
+    // step 1: (last-column symbol, row) pairs; stable partition by symbol -> psi
+    k_ibwt_elements<<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(d_bwt, n, origin, ctx->keys[0], ctx->ids[0]);
+    LAUNCHED();
+    {
+        const u32 blocks = (u32)std::min<u64>(ceil_div(n, 256 * 8), (u64)ctx->num_sms * 8);
+        k_digit_hist<256><<<std::max(blocks, 1u), 256, 0, ctx->stream>>>(ctx->keys[0], n, 0, 1, ctx->hist);
+        LAUNCHED();
+    }
+    int cur = 0;
+    if (int rc = run_sort(ctx, ctx->keys, ctx->ids, 0, n, 0, 1, &cur, nullptr, 0)) return rc;
+    const u32* psi1 = ctx->ids[cur];
+    // step 2: sublists between splitters
+    const u32 stride = 64;
+    const u32 head = origin + 1;
+    const u32 regular = (u32)ceil_div((u64)n + 1, stride);
+    const u32 nodes = regular + 1;
+    u32* dist[2] = {ctx->ranks, ctx->sa};
+    u32* next[2] = {ctx->isa, ctx->ids[cur ^ 1]};
+    k_ibwt_walk<false><<<(u32)ceil_div(nodes, 128), 128, 0, ctx->stream>>>(psi1, n, head, stride, regular, dist[0], next[0], nullptr,
+                                                                           nullptr, nullptr);
+    LAUNCHED();
+    // step 3: suffix sums of the sublist lengths along the splitter list (pointer jumping)
+    int w = 0;
+    for (u32 span = 1; span < nodes; span <<= 1) {
+        k_ibwt_jump<<<(u32)ceil_div(nodes, 256), 256, 0, ctx->stream>>>(dist[w], next[w], dist[w ^ 1], next[w ^ 1], nodes);
+        LAUNCHED();
+        w ^= 1;
+    }
+    k_ibwt_report<<<1, 1, 0, ctx->stream>>>(dist[w], regular, &ctx->mail_dev->count);
+    LAUNCHED();
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((u64)ctx->mail->count != (u64)n + 1) {
+        snprintf(ctx->err, sizeof(ctx->err), "inverse BWT: (bwt, origin) is not a forward transform (list covers %u of %llu rows)",
+                 ctx->mail->count, (unsigned long long)n + 1);
+        return DARK_BWT_E_INVALID_ARG;
+    }
+    // step 4: walk again, writing the text
+    k_ibwt_walk<true><<<(u32)ceil_div(nodes, 128), 128, 0, ctx->stream>>>(psi1, n, head, stride, regular, nullptr, nullptr, dist[w],
+                                                                          ctx->hist, d_text);
+    LAUNCHED();
+    CK(cudaEventRecord(eb, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ms_out) cudaEventElapsedTime(ms_out, ea, eb);
+    return DARK_BWT_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -838,6 +897,26 @@ int dark_bwt_forward_batch(dark_bwt_ctx* ctx, const uint8_t* const* texts, const
     }
     CK(cudaStreamSynchronize(ctx->copy_out));
     CK(cudaStreamSynchronize(ctx->copy_in));
+    return DARK_BWT_OK;
+}
+
+int dark_bwt_inverse_device(dark_bwt_ctx* ctx, const uint8_t* d_bwt, uint64_t n, uint64_t origin, uint8_t* d_text_out,
+                            float* ms_out) {
+    if (!ctx || !d_bwt || !d_text_out) return DARK_BWT_E_INVALID_ARG;
+    ctx->err[0] = 0;
+    return inverse_device(ctx, d_bwt, n, origin, d_text_out, ms_out);
+}
+
+int dark_bwt_inverse(dark_bwt_ctx* ctx, const uint8_t* bwt, uint64_t n, uint64_t origin, uint8_t* text_out) {
+    if (!ctx || !bwt || !text_out) return DARK_BWT_E_INVALID_ARG;
+    if (ctx->flags & DARK_BWT_F_DEVICE_ONLY) return DARK_BWT_E_INVALID_ARG;
+    if (n < 1 || n > ctx->capacity || n > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;
+    ctx->err[0] = 0;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->d_bwt, bwt, n, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = inverse_device(ctx, ctx->d_bwt, n, origin, ctx->d_text, nullptr)) return rc;
+    CK(cudaMemcpyAsync(text_out, ctx->d_text, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return DARK_BWT_OK;
 }
 

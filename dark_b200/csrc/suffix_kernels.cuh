@@ -862,6 +862,94 @@ k_emit_bwt_window(const u8* __restrict__ text, u32 n, const u32* __restrict__ sa
     }
 }
 
+// ---- inverse BWT (the unpack side, compress::bwt::decode at src/block/dc.rs:154-156) -------
+// The rows of the forward transform are the suffixes with end-of-text lowest, i.e. the sorted rotations of
+// T$ without the "$T" row.  With that row put back (row 0; its last symbol is bwt[origin]) and the row of
+// suffix 0 (row origin+1) ending in '$', a STABLE partition of the n real last-column symbols by value
+// gives psi: sorted slot q (= row q+1) <- the row whose last symbol it is.  Following psi from row
+// origin+1 spells T forwards: T[i] = first symbol of the i-th row visited.
+//   step 1  k_ibwt_elements: (symbol, row) pairs in row order            -> one radix pass -> psi
+//   step 2  k_ibwt_walk<false>: every STRIDE-th row (and the head) is a splitter; one thread walks from each
+//           splitter to the next: sublist length + successor splitter      (dependent random reads)
+//   step 3  k_ibwt_jump: pointer jumping over the splitter list only        (n/STRIDE nodes)
+//   step 4  k_ibwt_walk<true>: walk again, now writing T at the known offset
+__global__ void __launch_bounds__(256)
+k_ibwt_elements(const u8* __restrict__ bwt, u32 n, u32 origin, u64* __restrict__ keys, u32* __restrict__ rows) {
+    const u64 e = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (e >= n) return;
+    const u32 r = e == 0 ? 0u : (e <= origin ? (u32)e : (u32)e + 1u);
+    keys[e] = e == 0 ? bwt[origin] : bwt[r - 1];
+    rows[e] = r;
+}
+
+constexpr u32 kIbwtNil = 0xFFFFFFFFu;
+
+// first symbol of row r >= 1: the symbol whose bucket [base[c], base[c+1]) holds sorted slot r-1
+__device__ __forceinline__ u32 ibwt_first_symbol(const u32* s_base, u32 r) {
+    const u32 q = r - 1;
+    u32 lo = 0, hi = 255;  // largest c with s_base[c] <= q
+    while (lo < hi) {
+        const u32 mid = (lo + hi + 1) >> 1;
+        if (s_base[mid] <= q) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+k_ibwt_walk(const u32* __restrict__ psi1 /* psi[r] for r >= 1 at psi1[r-1] */, u32 n, u32 head, u32 stride, u32 regular,
+            u32* __restrict__ len, u32* __restrict__ next, const u32* __restrict__ dist, const u32* __restrict__ base,
+            u8* __restrict__ text_out) {
+    __shared__ u32 s_base[256];
+    if (WRITE) {
+        for (int i = threadIdx.x; i < 256; i += 128) s_base[i] = base[i];
+        __syncthreads();
+    }
+    const u32 s = blockIdx.x * 128 + threadIdx.x;
+    if (s > regular) return;  // splitters 0..regular-1 are rows s*stride; splitter `regular` is the head row
+    u32 r = s < regular ? s * stride : head;
+    if (s < regular && r == head) {  // the head row is owned by its own splitter
+        if (!WRITE) {
+            len[s] = 0;
+            next[s] = kIbwtNil;
+        }
+        return;
+    }
+    u64 pos = 0;
+    if (WRITE) pos = (u64)(n + 1) - dist[s];  // text position of this splitter's row
+    u32 cnt = 0;
+    do {
+        if (WRITE && r != 0 && pos + cnt < n) text_out[pos + cnt] = (u8)ibwt_first_symbol(s_base, r);
+        ++cnt;
+        r = r == 0 ? head : __ldg(psi1 + (r - 1));
+    } while (!(r % stride == 0 || r == head) && cnt <= n);  // cnt bound: corrupt input must not hang
+    if (!WRITE) {
+        len[s] = cnt;
+        // the sublist of row 0 ('$', the last node) ends the list: psi[0] wraps to the head
+        next[s] = (s == 0) ? kIbwtNil : (r == head ? regular : r / stride);
+    }
+}
+
+__global__ void k_ibwt_report(const u32* __restrict__ dist, u32 head_splitter, u32* __restrict__ out) { *out = dist[head_splitter]; }
+
+// one pointer-jumping round over the splitter list: suffix sums of the sublist lengths
+__global__ void __launch_bounds__(256)
+k_ibwt_jump(const u32* __restrict__ dist_in, const u32* __restrict__ next_in, u32* __restrict__ dist_out,
+            u32* __restrict__ next_out, u32 count) {
+    const u32 s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= count) return;
+    const u32 nx = next_in[s];
+    u32 d = dist_in[s];
+    u32 nn = kIbwtNil;
+    if (nx != kIbwtNil) {
+        d += dist_in[nx];
+        nn = next_in[nx];
+    }
+    dist_out[s] = d;
+    next_out[s] = nn;
+}
+
 // ---- verification (independent of the construction kernels) ------------------------------------
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_verify_scatter(const u32* __restrict__ sa, u32 n, u32* __restrict__ isa, unsigned long long* bad) {

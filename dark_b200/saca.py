@@ -113,6 +113,21 @@ class Constructor:
         origins = self.bwt_batch_into([t.ctypes.data for t in ts], [t.size for t in ts], [o.ctypes.data for o in outs])
         return list(zip(outs, origins))
 
+    # -- the unpack side: compress::bwt::decode(&input, origin, &mut suffixes)  (block/dc.rs:154-156) ---------
+    def inverse(self, bwt, origin):
+        """Original block (np.uint8[n]) from its BWT bytes and origin index."""
+        b = _as_u8(bwt)
+        out = np.empty(b.size, dtype=np.uint8)
+        _ffi.check(self._L.dark_bwt_inverse(self._ctx, b.ctypes.data if b.size else None, b.size, int(origin),
+                                            out.ctypes.data if b.size else None), self._ctx, "bwt::decode")
+        return out
+
+    def inverse_device(self, d_bwt, n, origin, d_text):
+        ms = ctypes.c_float(0)
+        _ffi.check(self._L.dark_bwt_inverse_device(self._ctx, d_bwt, int(n), int(origin), d_text, ctypes.byref(ms)), self._ctx,
+                   "bwt::decode")
+        return float(ms.value)
+
     # -- device-resident form (benches, pipelines that keep the block in HBM) ------------------
     def bwt_device(self, d_text, n, d_bwt, d_sa=None):
         """Raw device pointers (ints).  Returns origin; self.stats holds the device timings."""
@@ -160,6 +175,13 @@ class Constructor:
 
     def __exit__(self, *a):
         self.close()
+
+
+def decode(bwt, origin, device=0):
+    """`compress::bwt::decode(&input, origin, &mut suffixes)` collected: the original bytes."""
+    b = _as_u8(bwt)
+    with Constructor(max(b.size, 2), device=device) as con:
+        return con.inverse(b, origin)
 
 
 def transform(input, suf):

@@ -120,6 +120,14 @@ int dark_bwt_forward_batch(dark_bwt_ctx *ctx, const uint8_t *const *texts, const
 int dark_bwt_forward_device(dark_bwt_ctx *ctx, const uint8_t *d_text, uint64_t n, uint8_t *d_bwt_out,
                             uint64_t *origin_out, uint32_t *d_sa_out, dark_bwt_stats *stats);
 
+/* Inverse transform (the unpack side): text_out[0..n) from bwt[0..n) and origin — what
+ * `compress::bwt::decode(&input, origin, &mut suffixes)` yields at src/block/dc.rs:154-156 and
+ * src/block/raw.rs:98-100 (also saca.rs:405,424).  Host and device-buffer forms; 1 <= n <= capacity,
+ * origin < n.  DARK_BWT_E_INVALID_ARG if (bwt, origin) is not the forward transform of any text. */
+int dark_bwt_inverse(dark_bwt_ctx *ctx, const uint8_t *bwt, uint64_t n, uint64_t origin, uint8_t *text_out);
+int dark_bwt_inverse_device(dark_bwt_ctx *ctx, const uint8_t *d_bwt, uint64_t n, uint64_t origin, uint8_t *d_text_out,
+                            float *ms_out /* nullable */);
+
 /* Constructor::reuse — lends >= capacity host u32 words of scratch (DC distances in
  * block/dc.rs:51).  Allocated on first use; owned by the context. */
 int dark_bwt_reuse(dark_bwt_ctx *ctx, uint32_t **words_out, uint64_t *count_out);

@@ -327,3 +327,71 @@ def test_idempotent_context_reuse(saca, oracle, torch):
         bwt_o, origin_o = oracle.bwt_forward(t)
         assert origin == origin_o and np.array_equal(bwt, bwt_o)
     con.close()
+
+
+# ---- the unpack side: inverse BWT ---------------------------------------------------
+def test_inverse_known_answers(saca, torch):
+    # saca.rs:404-406: bwt::decode(&output, origin, suf) gives back the input of the KATs
+    for text, _, origin, bwt in KAT:
+        assert saca.decode(bwt, origin).tobytes() == text
+
+
+@pytest.mark.parametrize("sigma", [1, 2, 4, 256])
+def test_inverse_small_random_vs_oracle(con_small, oracle, sigma):
+    rng = np.random.default_rng(3000 + sigma)
+    for it in range(40):
+        n = int(rng.integers(1, 70)) if it < 25 else int(rng.integers(70, 9000))
+        t = rng.integers(0, sigma, n).astype(np.uint8)
+        if n >= 2:
+            bwt, origin = oracle.bwt_forward(t)
+        else:
+            bwt, origin = t.copy(), 0
+        back = con_small.inverse(bwt, origin)
+        assert np.array_equal(back, t), (sigma, n)
+        assert np.array_equal(back, oracle.bwt_decode(bwt, origin))
+
+
+@pytest.mark.parametrize("key", ["text:3:768771", "dna:1:1048576", "rep17:2:1048576", "mixed:4:1048576", "mixed:1000:4194304"])
+def test_inverse_medium_shapes_roundtrip(saca, oracle, torch, key):
+    from dark_b200 import synth
+    kind, seed, n = key.split(":")
+    t = synth.generate(kind, int(seed), int(n))
+    with saca.Constructor(t.size) as con:
+        bwt, origin = con.bwt(t)                     # forward on the GPU ...
+        assert np.array_equal(con.inverse(bwt, origin), t)   # ... and back
+        edge = EDGE[5]                                # all-equal bytes through the same context
+        b2, o2 = oracle.bwt_forward(edge)
+        assert con.inverse(b2, o2).tobytes() == edge
+
+
+def test_inverse_rejects_inconsistent_input_without_hanging(saca, oracle, torch):
+    from dark_b200 import DarkBwtError, synth
+    t = synth.generate("text", 21, 50000)
+    bwt, origin = oracle.bwt_forward(t)
+    with saca.Constructor(t.size) as con:
+        with pytest.raises(DarkBwtError):
+            con.inverse(bwt, t.size)                  # origin out of range
+        wrong = (origin + 12345) % t.size
+        try:                                          # a wrong origin either fails loudly or decodes to another text,
+            back = con.inverse(bwt, wrong)            # but never hangs and never returns the original
+            assert not np.array_equal(back, t)
+        except DarkBwtError:
+            pass
+        assert np.array_equal(con.inverse(bwt, origin), t)
+
+
+def test_inverse_large_device_resident(saca, golden, torch):
+    """C2 (256 MiB DNA): forward then inverse, both device-resident; the inverse restores the block."""
+    from dark_b200 import synth, _ffi
+    n = 1 << 28
+    t = synth.generate("dna", 1, n)
+    con = saca.Constructor(n, flags=_ffi.F_DEVICE_ONLY)
+    dt = torch.from_numpy(t).cuda()
+    db = torch.empty(n, dtype=torch.uint8, device="cuda")
+    origin = con.bwt_device(dt.data_ptr(), n, db.data_ptr())
+    assert origin == golden["dna:1:268435456"]["origin"]
+    dback = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    ms = con.inverse_device(db.data_ptr(), n, origin, dback.data_ptr())
+    assert torch.equal(dback, dt)
+    print("inverse BWT 256 MiB: %.2f ms (%.1f GB/s)" % (ms, n / ms / 1e6))
+    con.close()
