@@ -82,7 +82,8 @@ struct dark_bwt_ctx {
     size_t arena_bytes = 0;
     u64* keys[2] = {nullptr, nullptr};
     u32* ids[2] = {nullptr, nullptr};
-    u32* ranks = nullptr;
+    u32* ranks = nullptr;      // rank of each active suffix's group (current list)
+    u32* ranks_alt = nullptr;  // the re-rank of rounds >= 1 reads `ranks` and writes here, then they swap
     u32* isa = nullptr;
     u32* sa = nullptr;
     u8* d_text = nullptr;  // host-entry staging
@@ -300,9 +301,11 @@ int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32
     CK(cudaMemsetAsync(ctx->scan_words, 0, sizeof(u64) * kScanWordsPerTile * tiles, ctx->stream));
     ScanTileState ts{ctx->scan_words};
     k_rerank<kScanThreads, kScanItems, ROUND0, PAIRS><<<tiles, kScanThreads, 0, ctx->stream>>>(
-        keys, ids, m, n, K, kb, ctx->isa, sa, out_ids, ctx->ranks, ts, counter, &ctx->mail_dev->count, sink.ids, sink.vals,
+        keys, ids, ROUND0 ? nullptr : ctx->ranks, m, n, K, kb, ctx->isa, sa, out_ids, ROUND0 ? ctx->ranks : ctx->ranks_alt, ts, counter,
+        &ctx->mail_dev->count, sink.ids, sink.vals,
         ctx->bucket_hist, sink.shift, text, bwt_inline, &ctx->mail_dev->origin);
     LAUNCHED();
+    if (!ROUND0) std::swap(ctx->ranks, ctx->ranks_alt);
     return 0;
 }
 
@@ -481,7 +484,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     if (st) st->initial_symbols = K0;
 
     const int kb = bit_length(n);  // rank2 = isa+1 in [0, n]
-    const int key_bits = kb + bit_length((u64)n - 1);
+    const int key_bits = kb + bit_length(((u64)n - 1) >> 1);  // high part = rank >> 1 (suffix_kernels.cuh, k_rerank)
     const int passes_r = (key_bits + kRadixBits - 1) / kRadixBits;
 
     sp = span_begin(ctx, PH_RERANK);
@@ -730,7 +733,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     };
     const size_t o_keys0 = carve(N * 8 + 1024), o_keys1 = carve(N * 8 + 1024);  // slack: pair lists are split at a 64-aligned offset
     const size_t o_ids0 = carve(N * 4 + 16), o_ids1 = carve(N * 4 + 16);
-    const size_t o_ranks = carve(N * 4 + 16), o_isa = carve(N * 4 + 16), o_sa = carve(N * 4 + 16);
+    const size_t o_ranks = carve(N * 4 + 16), o_ranks2 = carve(N * 4 + 16), o_isa = carve(N * 4 + 16), o_sa = carve(N * 4 + 16);
     const size_t o_text = staging ? carve(N + 16) : 0, o_bwt = staging ? carve(N + 16) : 0;
     const size_t o_text2 = staging ? carve(N + 16) : 0, o_bwt2 = staging ? carve(N + 16) : 0;
     const size_t o_hist = carve(sizeof(u32) * kMaxPasses * kRadix);
@@ -759,6 +762,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     ctx->ids[0] = (u32*)(base + o_ids0);
     ctx->ids[1] = (u32*)(base + o_ids1);
     ctx->ranks = (u32*)(base + o_ranks);
+    ctx->ranks_alt = (u32*)(base + o_ranks2);
     ctx->isa = (u32*)(base + o_isa);
     ctx->sa = (u32*)(base + o_sa);
     ctx->d_text = staging ? (u8*)(base + o_text) : nullptr;

@@ -204,7 +204,7 @@ k_build_keys(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m, 
         for (int k = 0; k < ITEMS; ++k) {
             const u64 p = base + k * THREADS + tid;
             if (p < m) {
-                const u64 key = ((u64)ld_stream(ranks + p) << kb) | r2[k];
+                const u64 key = ((u64)(ld_stream(ranks + p) >> 1) << kb) | r2[k];  // >>1: see k_rerank
                 keys_out[p] = key;
                 hist_add_key(s_hist, key, 0, num_passes);
             }
@@ -259,7 +259,7 @@ k_build_keys_search(const u32* __restrict__ ids, const u32* __restrict__ ranks, 
             }
             r2 = slot + 1;
         }
-        const u64 key = ((u64)ranks[p] << kb) | r2;
+        const u64 key = ((u64)(ranks[p] >> 1) << kb) | r2;
         keys_out[p] = key;
         hist_add_key(s_hist, key, 0, num_passes);
     }
@@ -309,8 +309,8 @@ __device__ __forceinline__ u64 scan_pack(u32 flag, u32 value) { return ((u64)fla
 // bucket histogram (id >> pair_shift) to pair_hist for the bucketed scatter that follows.
 template <int THREADS, int ITEMS, bool ROUND0, bool PAIRS>
 __global__ void __launch_bounds__(THREADS, 2)
-k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n, int K, int kb, u32* __restrict__ isa,
-         u32* __restrict__ sa, u32* __restrict__ out_ids, u32* __restrict__ out_ranks, ScanTileState ts,
+k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* __restrict__ ranks_in, u32 m, u32 n, int K, int kb,
+         u32* __restrict__ isa, u32* __restrict__ sa, u32* __restrict__ out_ids, u32* __restrict__ out_ranks, ScanTileState ts,
          u32* __restrict__ tile_counter, u32* __restrict__ out_count, u32* __restrict__ pair_ids,
          u32* __restrict__ pair_vals, u32* __restrict__ pair_hist, int pair_shift, const u8* __restrict__ text,
          u8* __restrict__ bwt_inline, u64* __restrict__ origin) {
@@ -364,6 +364,29 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
     if (ROUND0) {
         id[0] = (p0 > 0 && p0 - 1 < m) ? ids[p0 - 1] : 0;
         id[ITEMS + 1] = (p0 + ITEMS < m) ? ids[p0 + ITEMS] : 0;
+    }
+
+    // Old group ranks (rounds >= 1).  The key carries only rank>>1 in its high part — active groups
+    // have at least two members, so their head slots differ by >= 2 and rank>>1 is still strictly
+    // increasing from group to group; that saves a key bit (8 -> 7 radix passes at n = 2^28).  The exact
+    // rank comes from the list itself: sorting permutes elements only inside their group, and every
+    // member of a group holds the same rank, so ranks_in[p] is the rank of whatever lands at index p.
+    u32 rold[ITEMS];
+    if (!ROUND0) {
+        if (p0 + ITEMS <= m) {
+            const uint4* rv = reinterpret_cast<const uint4*>(ranks_in + p0);
+#pragma unroll
+            for (int k = 0; k < ITEMS / 4; ++k) {
+                const uint4 q = rv[k];
+                rold[4 * k] = q.x;
+                rold[4 * k + 1] = q.y;
+                rold[4 * k + 2] = q.z;
+                rold[4 * k + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) rold[k] = (p0 + k < m) ? ranks_in[p0 + k] : 0u;
+        }
     }
 
     // head flags for p0 .. p0+ITEMS (the last one is the look-ahead of item ITEMS-1)
@@ -520,7 +543,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 m, u32 n
         if (p < m) {
             if ((oldh >> k) & 1) run.gs1 = (u32)p + 1;
             if ((newh >> k) & 1) run.hs1 = (u32)p + 1;
-            const u32 r_old = ROUND0 ? 0u : (u32)(key[k + 1] >> kb);
+            const u32 r_old = ROUND0 ? 0u : rold[k];
             const u32 r_new = r_old + (run.hs1 - run.gs1);
             const u32 sid = id[k + 1];
             const bool single = ((newh >> k) & 1) && ((newh >> (k + 1)) & 1);
