@@ -59,7 +59,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -229,7 +229,7 @@ def run_native(args, rank, local_rank, world):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": desc, "block_bytes": n, "blocks_per_step": world, "sharding": "independent blocks, no collective",
-                       "l2": "inputs larger than L2 (text %d MiB, working set ~%.1f GiB): no flush between steps" % (n >> 20, 38.5 * n / 2**30),
+                       "l2": "inputs larger than L2 (text %d MiB, working set ~%.1f GiB): no flush between steps" % (n >> 20, 46.5 * n / 2**30),
                        "origin": origin, "sigma": stats["sigma"], "symbols_per_key": stats["symbols_per_key"],
                        "rounds": stats["rounds"], "active_per_round": stats["active"], "passes_per_round": stats["passes"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": n + 8,

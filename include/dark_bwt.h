@@ -92,7 +92,7 @@ typedef struct dark_bwt_stats {
 } dark_bwt_stats;
 
 /* Constructor::new — allocates every device buffer for blocks of up to max_n bytes on
- * CUDA device `device` (about 38.5 * max_n bytes of HBM).  Nothing is allocated later. */
+ * CUDA device `device` (about 46.5 * max_n bytes of HBM, 42.5 with DARK_BWT_F_DEVICE_ONLY).  Nothing is allocated later. */
 int dark_bwt_create(uint64_t max_n, int device, dark_bwt_ctx **out);
 int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx **out);
 
