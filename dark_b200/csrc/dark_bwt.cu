@@ -178,10 +178,12 @@ int launch_pass_kernel(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* k
     auto kern = k_onesweep_pass<THREADS, ITEMS, MINBLOCKS, ILP, StatusT, ALIGNED>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));  // per device
     static const bool by_block_index = getenv("DARK_BWT_TILE_BY_BLOCKIDX") != nullptr;
+    const char* ke = getenv("DARK_BWT_PASS_KNOCKOUT");  // measurement only: skip phases (1 look-back, 2 ranking, 4 stores)
+    const u32 knock = ke ? (u32)atoi(ke) : 0u;
     // persistent grid: as many CTAs as stay resident (SMs x MINBLOCKS), each claiming tiles until none are left
     const u32 grid = by_block_index ? tiles : std::min<u32>(tiles, (u32)ctx->num_sms * MINBLOCKS);
     kern<<<grid, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base, (StatusT*)ctx->sort_status,
-                                                        by_block_index ? nullptr : counter, ctx->pass_trace, prev_text, n_text);
+                                                        by_block_index ? nullptr : counter, ctx->pass_trace, prev_text, n_text, knock);
     LAUNCHED();
     return 0;
 }
@@ -335,7 +337,7 @@ int bucket_scan(dark_bwt_ctx* ctx) {
     return 0;
 }
 int bucket_scatter(dark_bwt_ctx* ctx, const u32* out_ids, const u32* out_vals, u32 upper) {
-    k_scatter_ranks_counted<256><<<(u32)ceil_div(upper, 256), 256, 0, ctx->stream>>>(out_ids, out_vals, &ctx->scalars->pair_total,
+    k_scatter_ranks_counted<256><<<(u32)ceil_div(ceil_div(upper, 4), 256), 256, 0, ctx->stream>>>(out_ids, out_vals, &ctx->scalars->pair_total,
                                                                                       ctx->isa);
     LAUNCHED();
     return 0;

@@ -228,7 +228,8 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
                                               const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
                                               u32* __restrict__ vals_out, const u32 tile, const u32 nvalid, const int shift,
                                               const u32* __restrict__ digit_base, StatusT* __restrict__ status,
-                                              long long* __restrict__ trace, const u8* __restrict__ prev_text, const u32 n_text) {
+                                              long long* __restrict__ trace, const u8* __restrict__ prev_text, const u32 n_text, const u32 knock) {
+    // knock != 0 (tools/sort_bench.py KNOCKOUT only): phases are skipped to measure what they cost; output is garbage
     // trace != nullptr (tools/pass_trace.py only): thread 0 stamps clock64() at the phase boundaries
 #define DARK_STAMP(i) do { if (trace && threadIdx.x == 0) trace[(size_t)tile * 12 + (i)] = clock64(); } while (0)
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
@@ -292,7 +293,8 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
         // ILP items stay in flight per warp.
         if (k >= ILP) asm volatile("" : "+r"(d) : "r"(rank2[(k - ILP) / 2]));
         u32 peers = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
-        peers = match_digit_bits(peers, d);
+        if (knock & 2u) peers = 1u << lane;
+        else peers = match_digit_bits(peers, d);
         const u32 prev = whist[d];  // every lane reads (padding lanes harmlessly), then the group's lowest lane bumps
         const u32 below = peers & lt;
         const u32 r = prev + __popc(below);
@@ -357,7 +359,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
     // nearest inclusive prefix is 10-25 tiles back: walking them one load at a time cost 34 % of the
     // tile time (profiles/r1_pass_trace_v3.log); 8 predecessors are read per round trip.
     if (tid < kRadix) {
-        if (tile > 0) {
+        if (tile > 0 && !(knock & 1u)) {
             lb.finish(status, tid);
             st_relaxed(status + (size_t)tile * kRadix + tid, ((StatusT)2 << ST::kShift) | (lb.excl + count));
         }
@@ -373,8 +375,10 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
         if (FULL || p < nvalid) {
             const u64 kk = s.keys[p];
             const u32 idx = s.global_off[digit(kk)] + p;
-            keys_out[idx] = kk;
-            vals_out[idx] = s.vals[p];
+            if (!(knock & 4u)) {
+                keys_out[idx] = kk;
+                vals_out[idx] = s.vals[p];
+            }
         }
     }
     DARK_STAMP(7);
@@ -391,7 +395,7 @@ __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
                 u32* __restrict__ vals_out, u32 m, int shift, const u32* __restrict__ digit_base,
                 StatusT* __restrict__ status, u32* __restrict__ tile_counter, long long* __restrict__ trace,
-                const u8* __restrict__ prev_text, u32 n_text) {
+                const u8* __restrict__ prev_text, u32 n_text, u32 knock) {
     static_assert(THREADS >= kRadix && THREADS % 32 == 0, "one thread per digit is assumed");
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
     constexpr int TILE = Smem::kTile;
@@ -426,10 +430,10 @@ k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in
         const u32 nvalid = (u32)min((u64)TILE, (u64)m - (u64)tile * TILE);
         if (nvalid == TILE)
             onesweep_tile<THREADS, ITEMS, ILP, StatusT, ALIGNED, true>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid,
-                                                                              shift, digit_base, status, trace, prev_text, n_text);
+                                                                              shift, digit_base, status, trace, prev_text, n_text, knock);
         else
             onesweep_tile<THREADS, ITEMS, ILP, StatusT, ALIGNED, false>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid,
-                                                                               shift, digit_base, status, trace, prev_text, n_text);
+                                                                               shift, digit_base, status, trace, prev_text, n_text, knock);
         if (tile_counter == nullptr) break;
         __syncthreads();  // the scatter has read the shared tile: it may be overwritten now
     }

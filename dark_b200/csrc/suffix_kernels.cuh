@@ -656,11 +656,25 @@ k_scatter_ranks(const u32* __restrict__ act_ids, const u32* __restrict__ act_ran
     if (p < m) isa[ld_stream(act_ids + p)] = ld_stream(act_ranks + p);
 }
 
+// Four pairs per thread (128-bit loads): the stores are random inside the bucket's L2-resident slice, so
+// what matters is how many of them each thread keeps in flight.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_scatter_ranks_counted(const u32* __restrict__ ids, const u32* __restrict__ vals, const u32* __restrict__ count, u32* __restrict__ isa) {
-    const u64 p = (u64)blockIdx.x * THREADS + threadIdx.x;
-    if (p < *count) isa[ld_stream(ids + p)] = ld_stream(vals + p);
+    const u32 total = *count;
+    const u64 p = ((u64)blockIdx.x * THREADS + threadIdx.x) * 4;
+    if (p >= total) return;
+    if (p + 4 <= total) {
+        uint4 i4, v4;
+        asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(i4.x), "=r"(i4.y), "=r"(i4.z), "=r"(i4.w) : "l"(ids + p));
+        asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w) : "l"(vals + p));
+        isa[i4.x] = v4.x;
+        isa[i4.y] = v4.y;
+        isa[i4.z] = v4.z;
+        isa[i4.w] = v4.w;
+    } else {
+        for (u64 q = p; q < total; ++q) isa[ids[q]] = vals[q];
+    }
 }
 
 // Selective rank fill (few survivors after round 0): the next round reads isa[i+h] for the
