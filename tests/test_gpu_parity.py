@@ -395,3 +395,26 @@ def test_inverse_large_device_resident(saca, golden, torch):
     assert torch.equal(dback, dt)
     print("inverse BWT 256 MiB: %.2f ms (%.1f GB/s)" % (ms, n / ms / 1e6))
     con.close()
+
+
+def test_two_contexts_in_two_host_threads(saca, oracle, torch):
+    """Distinct contexts are independent (one context per host thread): two threads drive
+    two contexts on the same GPU at once (ctypes drops the GIL during the call)."""
+    import threading
+    from dark_b200 import synth
+    blocks = [synth.generate("mixed", 31, 700001), synth.generate("dna", 32, 900001)]
+    expect = [oracle.bwt_forward(b) for b in blocks]
+    results = [None, None]
+
+    def work(i):
+        with saca.Constructor(blocks[i].size) as con:
+            for _ in range(3):
+                results[i] = con.bwt(blocks[i])
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for (bwt, origin), (bwt_o, origin_o) in zip(results, expect):
+        assert origin == origin_o and np.array_equal(bwt, bwt_o)
