@@ -42,6 +42,18 @@ WORKLOADS = {
 }
 
 
+def measured_pass_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one full-size radix-pass launch (ncu --set full capture
+    committed under profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_pass_traffic.json")) as f:
+            t = json.load(f)
+        return {"bytes_per_launch": t["dram__bytes_read.sum"] + t["dram__bytes_write.sum"], "pairs_per_launch": t["pairs_per_launch"],
+                "algorithmic_bytes_per_launch": t["algorithmic_bytes_per_launch"]}
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -241,7 +253,8 @@ def run_native(args, rank, local_rank, world):
                          "achieved": pass_gbs, "peak": peak, "unit": "GB/s", "frac": pass_gbs / peak, "peak_source": peak_src,
                          "launches_per_step": agg["passes"] / args.steps,
                          "avg_launch_ms": agg["pass_ms"] / max(1, agg["passes"]),
-                         "traffic": None,
+                         "traffic": (measured_pass_traffic() or {}).get("bytes_per_launch"),
+                         "traffic_detail": measured_pass_traffic(),
                          "path_b_alg_per_byte": balg_per_byte, "path_achieved": path_gbs, "path_frac": path_gbs / peak,
                          "path_frac_of_8TBs": path_gbs / 8000.0},
             "phases_ms_per_step": {k: agg[k] / args.steps for k in ("device_ms", "init_ms", "sort_ms", "keybuild_ms",
