@@ -220,6 +220,7 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
         case 0: V(256, 16, 2, 2);
         case 2: V(256, 12, 3, 2);
         case 5: V(512, 12, 2, 2);
+        case 42: V(384, 16, 2, 2);
         default: V(256, 16, 3, 2);  // 1
     }
 #undef V
