@@ -641,7 +641,8 @@ int inverse_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, u64 origin64, u8
     if (int rc = run_sort(ctx, ctx->keys, ctx->ids, 0, n, 0, 1, &cur, nullptr, 0)) return rc;
     const u32* psi1 = ctx->ids[cur];
     // step 2: sublists between splitters
-    const u32 stride = 64;
+    const char* se = getenv("DARK_BWT_IBWT_STRIDE");  // rows between splitters (sweeps only)
+    const u32 stride = se ? (u32)std::max(2, atoi(se)) : 64u;
     const u32 head = origin + 1;
     const u32 regular = (u32)ceil_div((u64)n + 1, stride);
     const u32 nodes = regular + 1;

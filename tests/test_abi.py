@@ -77,3 +77,14 @@ def test_product_never_touches_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "liboracle" not in text and "oracle/" not in text.replace(
                     "oracle/gen.c; tests", ""), f
+
+
+def test_cpp_mirror_compiles_and_links(lib, tmp_path):
+    """The C++ host-side mirror of saca::Constructor (dark_b200/csrc/saca.hpp) builds against the C ABI."""
+    import subprocess
+    from dark_b200 import _ffi
+    exe = tmp_path / "saca_cpp_demo"
+    libdir = os.path.dirname(_ffi.lib_path())
+    subprocess.check_call(["g++", "-std=c++17", "-I", ROOT, os.path.join(ROOT, "examples", "saca_cpp_demo.cpp"), "-L", libdir,
+                           "-ldark_bwt", f"-Wl,-rpath,{libdir}", "-o", str(exe)])
+    assert exe.exists()

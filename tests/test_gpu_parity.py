@@ -418,3 +418,16 @@ def test_two_contexts_in_two_host_threads(saca, oracle, torch):
         t.join()
     for (bwt, origin), (bwt_o, origin_o) in zip(results, expect):
         assert origin == origin_o and np.array_equal(bwt, bwt_o)
+
+
+def test_cpp_mirror_runs_the_reference_known_answers(torch, tmp_path):
+    """examples/saca_cpp_demo.cpp: the C++ mirror of saca::Constructor on saca.rs:411-412, on the GPU."""
+    import subprocess
+    from dark_b200 import _ffi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "saca_cpp_demo"
+    libdir = os.path.dirname(_ffi.lib_path())
+    subprocess.check_call(["g++", "-std=c++17", "-I", root, os.path.join(root, "examples", "saca_cpp_demo.cpp"), "-L", libdir,
+                           "-ldark_bwt", f"-Wl,-rpath,{libdir}", "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), (out.returncode, out.stdout, out.stderr)
