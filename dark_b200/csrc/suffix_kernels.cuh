@@ -390,43 +390,47 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     }
 
     // head flags for p0 .. p0+ITEMS (the last one is the look-ahead of item ITEMS-1)
-    const u64 short_from = (u64)n >= (u64)K ? (u64)n - K + 1 : 0;  // suffix i is "short" (key padded) iff i >= short_from
+    const u32 short_from = n >= (u32)K ? n - (u32)K + 1u : 0u;  // suffix i is "short" (key padded) iff i >= short_from
+    const u32 navail = p0 >= m ? 0u : (u32)min((u64)ITEMS + 1, (u64)m - p0);  // of p0 .. p0+ITEMS, how many are inside the list
+    const u32 nvalid = min(navail, (u32)ITEMS);                                // ... of this thread's own ITEMS elements
+    u64 hi[ITEMS + 2];  // the compared key part: bits above kb
+#pragma unroll
+    for (int k = 0; k < ITEMS + 2; ++k) hi[k] = key[k] >> kb;
     u32 newh = 0, oldh = 0;  // bit k: element p0+k starts a new / an old group
 #pragma unroll
     for (int k = 0; k <= ITEMS; ++k) {
-        const u64 p = p0 + k;
         bool nh, oh;
-        if (p >= m) {
-            nh = true;
-            oh = true;
-        } else if (p == 0) {
-            nh = true;
-            oh = true;
+        if (ROUND0) {
+            // round 0 sorted only the bits above kb (pass pruning): ties on those bits are groups
+            nh = hi[k + 1] != hi[k] || id[k + 1] >= short_from || id[k] >= short_from;
+            oh = false;
         } else {
-            if (ROUND0) {
-                // round 0 sorted only the bits above kb (pass pruning): ties on those bits are groups
-                nh = (key[k + 1] >> kb) != (key[k] >> kb) || id[k + 1] >= short_from || id[k] >= short_from;
-                oh = false;
-            } else {
-                nh = key[k + 1] != key[k];
-                oh = (key[k + 1] >> kb) != (key[k] >> kb);
-            }
+            nh = key[k + 1] != key[k];
+            oh = hi[k + 1] != hi[k];
         }
         newh |= (nh ? 1u : 0u) << k;
         oldh |= (oh ? 1u : 0u) << k;
     }
+    // list boundaries: position 0 and everything from m on are heads
+    if (p0 == 0) {
+        newh |= 1u;
+        oldh |= 1u;
+    }
+    if (navail < (u32)ITEMS + 1u) {  // p0+k >= m for k >= navail
+        const u32 tail = ~((1u << navail) - 1u) & ((2u << ITEMS) - 1u);
+        newh |= tail;
+        oldh |= tail;
+    }
 
-    // thread aggregate
+    // thread aggregate, from the flag words: latest old/new head among the valid elements, survivors
     ScanTriple agg = {0u, 0u, 0u};
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const u64 p = p0 + k;
-        if (p < m) {
-            if ((oldh >> k) & 1) agg.gs1 = (u32)p + 1;
-            if ((newh >> k) & 1) agg.hs1 = (u32)p + 1;
-            const bool single = ((newh >> k) & 1) && ((newh >> (k + 1)) & 1);
-            agg.cnt += single ? 0u : 1u;
-        }
+    {
+        const u32 vmask = (1u << nvalid) - 1u;
+        const u32 oh = oldh & vmask, nh = newh & vmask;
+        if (oh) agg.gs1 = (u32)p0 + (32u - __clz(oh));  // index of the highest set bit, plus one
+        if (nh) agg.hs1 = (u32)p0 + (32u - __clz(nh));
+        const u32 singles = newh & (newh >> 1) & vmask;  // head whose successor is a head too
+        agg.cnt = nvalid - __popc(singles);
     }
     // block-wide exclusive scan of the thread aggregates
     ScanTriple incl = agg;
