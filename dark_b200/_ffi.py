@@ -16,7 +16,7 @@ F_DEFAULT, F_NO_ALPHABET_PACKING, F_DEVICE_ONLY = 0, 1, 2
 SYMBOLS = [
     "dark_bwt_abi_version", "dark_bwt_create", "dark_bwt_create_ex", "dark_bwt_capacity", "dark_bwt_forward",
     "dark_bwt_forward_batch", "dark_bwt_forward_device", "dark_bwt_inverse", "dark_bwt_inverse_device", "dark_bwt_reuse", "dark_bwt_destroy", "dark_bwt_strerror", "dark_bwt_last_error",
-    "dark_bwt_stream", "dark_bwt_sort_pairs_device", "dark_bwt_verify_sa_device", "dark_bwt_emit_device",
+    "dark_bwt_stream", "dark_bwt_sort_pairs_device", "dark_bwt_verify_sa_device", "dark_bwt_emit_device", "dark_bwt_lcp_profile_device",
     "dark_bwt_synth",
 ]
 
@@ -95,6 +95,7 @@ def lib():
                                              ctypes.POINTER(ctypes.c_float)]
     L.dark_bwt_verify_sa_device.argtypes = [vp, vp, u64, vp, ctypes.POINTER(u64)]
     L.dark_bwt_emit_device.argtypes = [vp, vp, u64, vp, vp, ctypes.POINTER(u64)]
+    L.dark_bwt_lcp_profile_device.argtypes = [vp, vp, u64, vp, ctypes.POINTER(u64), ctypes.POINTER(u32), ctypes.POINTER(u64)]
     L.dark_bwt_synth.argtypes = [ctypes.c_char_p, u64, vp, u64]
     _lib = L
     return L

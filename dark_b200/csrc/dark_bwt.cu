@@ -1004,6 +1004,38 @@ int dark_bwt_debug_trace(dark_bwt_ctx* ctx, long long* d_trace) {
     return DARK_BWT_OK;
 }
 
+int dark_bwt_lcp_profile_device(dark_bwt_ctx* ctx, const uint8_t* d_text, uint64_t n64, const uint32_t* d_sa, uint64_t* m_out,
+                                uint32_t* rounds_out, uint64_t* max_lcp_out) {
+    if (!ctx || !d_text || !d_sa || !m_out || !rounds_out || !max_lcp_out) return DARK_BWT_E_INVALID_ARG;
+    if (n64 < 2 || n64 > ctx->capacity) return DARK_BWT_E_INVALID_N;
+    if (((uintptr_t)d_text) & 7) return DARK_BWT_E_INVALID_ARG;  // 64-bit text loads
+    ctx->err[0] = 0;
+    CK(cudaSetDevice(ctx->device));
+    const u32 n = (u32)n64;
+    u32* lcp = ctx->ranks;                                             // scratch: n u32
+    unsigned long long* buckets = (unsigned long long*)ctx->keys[0];  // scratch: 64 counters
+    u32* dmax = (u32*)(buckets + 64);
+    CK(cudaMemsetAsync(buckets, 0, 65 * sizeof(unsigned long long), ctx->stream));
+    k_lcp_direct<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(d_text, n, d_sa, lcp);
+    LAUNCHED();
+    k_lcp_buckets<256><<<(u32)std::min<u64>(ceil_div(n, 256 * 8), (u64)ctx->num_sms * 8), 256, 0, ctx->stream>>>(lcp, n, buckets, dmax);
+    LAUNCHED();
+    unsigned long long host[65];
+    CK(cudaMemcpyAsync(host, buckets, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int top = 0;
+    for (int k = 0; k < 64; ++k)
+        if (host[k]) top = k + 1;
+    unsigned long long run = 0;
+    for (int k = 63; k >= 0; --k) {
+        run += host[k];
+        m_out[k] = k < top ? run : 0;
+    }
+    *rounds_out = (uint32_t)top;
+    *max_lcp_out = (uint64_t)(host[64] & 0xFFFFFFFFull);
+    return DARK_BWT_OK;
+}
+
 int dark_bwt_emit_device(dark_bwt_ctx* ctx, const uint8_t* d_text, uint64_t n, const uint32_t* d_sa, uint8_t* d_bwt_out,
                          uint64_t* origin_out) {
     if (!ctx || !d_text || !d_sa || !d_bwt_out || !origin_out) return DARK_BWT_E_INVALID_ARG;

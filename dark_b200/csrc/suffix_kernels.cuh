@@ -991,6 +991,68 @@ k_ibwt_jump(const u32* __restrict__ dist_in, const u32* __restrict__ next_in, u3
     next_out[s] = nn;
 }
 
+// ---- LCP profile: the data-defined round structure m_r ------------------------
+// LCP[j] = lcp(SA[j-1], SA[j]) by direct comparison, 8 bytes per step (two aligned 64-bit loads and a
+// funnel shift per side; the text is read through L1/L2).  Work is sum(LCP)/8 steps: fine as a tool even
+// for the period-17 block (mean LCP 5,254).  Then v_j = max(LCP[j], LCP[j+1]) is bucketed by
+// floor(log2(v/8)); m_r of the profiler is the suffix sum of the buckets.
+__device__ __forceinline__ u64 load_u64_unaligned(const u8* __restrict__ text, u64 pos, u64 n) {
+    // bytes text[pos .. pos+8) little-endian, zero beyond n (callers stop at the end of either suffix)
+    const u64 base = pos & ~7ull;
+    const u64* w = reinterpret_cast<const u64*>(text) + (base >> 3);
+    const u64 lo = base < n ? __ldg(w) : 0ull;  // reads up to 7 bytes past n only inside the same aligned word
+    const unsigned sh = (unsigned)(pos & 7) * 8;
+    if (sh == 0) return lo;
+    const u64 hi = base + 8 < n ? __ldg(w + 1) : 0ull;
+    return (lo >> sh) | (hi << (64 - sh));
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_lcp_direct(const u8* __restrict__ text, u32 n, const u32* __restrict__ sa, u32* __restrict__ lcp) {
+    const u64 j = (u64)blockIdx.x * THREADS + threadIdx.x;
+    if (j >= n) return;
+    if (j == 0) {
+        lcp[0] = 0;
+        return;
+    }
+    const u64 a = sa[j - 1], b = sa[j];
+    const u64 limit = (u64)n - max(a, b);  // the shorter suffix ends here
+    u64 l = 0;
+    while (l < limit) {
+        const u64 x = load_u64_unaligned(text, a + l, n) ^ load_u64_unaligned(text, b + l, n);
+        if (x) {
+            l += (u64)(__ffsll((long long)x) - 1) >> 3;  // first differing byte (little-endian)
+            break;
+        }
+        l += 8;
+    }
+    lcp[j] = (u32)min(l, limit);
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_lcp_buckets(const u32* __restrict__ lcp, u32 n, unsigned long long* __restrict__ buckets /*[64]*/, u32* __restrict__ max_out) {
+    __shared__ unsigned long long s_b[64];
+    __shared__ u32 s_max;
+    if (threadIdx.x < 64) s_b[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * THREADS;
+    u32 mx = 0;
+    for (u64 j = (u64)blockIdx.x * THREADS + threadIdx.x; j < n; j += stride) {
+        const u32 cur = lcp[j];
+        const u32 nxt = j + 1 < n ? lcp[j + 1] : 0u;
+        const u32 v = max(cur, nxt);
+        mx = max(mx, cur);
+        if (v >= 8) atomicAdd(&s_b[31 - __clz(v >> 3)], 1ull);
+    }
+    atomicMax(&s_max, mx);
+    __syncthreads();
+    if (threadIdx.x < 64 && s_b[threadIdx.x]) atomicAdd(&buckets[threadIdx.x], s_b[threadIdx.x]);
+    if (threadIdx.x == 0) atomicMax(max_out, s_max);
+}
+
 // ---- verification (independent of the construction kernels) ------------------------------------
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_verify_scatter(const u32* __restrict__ sa, u32 n, u32* __restrict__ isa, unsigned long long* bad) {

@@ -142,6 +142,19 @@ class Constructor:
                    "verify_sa")
         return int(bad.value)
 
+    def lcp_profile_device(self, d_text, n, d_sa):
+        """SURVEY §8(d) profile on the GPU: dict(R, m[r], sum_m, max_lcp, b, P, b_alg)."""
+        m = (ctypes.c_uint64 * 64)()
+        rounds, mx = ctypes.c_uint32(0), ctypes.c_uint64(0)
+        _ffi.check(self._L.dark_bwt_lcp_profile_device(self._ctx, d_text, int(n), d_sa, m, ctypes.byref(rounds), ctypes.byref(mx)),
+                   self._ctx, "lcp_profile")
+        R = int(rounds.value)
+        ms = [int(m[i]) for i in range(R)]
+        b = int(n).bit_length()                      # ceil(log2(n+1))
+        P = (2 * b + 7) // 8
+        return {"R": R, "m": ms, "sum_m": sum(ms), "max_lcp": int(mx.value), "b": b, "P": P,
+                "b_alg": 243.0 * n + (48.0 + 24.0 * P) * sum(ms)}
+
     def emit_device(self, d_text, n, d_sa, d_bwt):
         origin = ctypes.c_uint64(0)
         _ffi.check(self._L.dark_bwt_emit_device(self._ctx, d_text, int(n), d_sa, d_bwt, ctypes.byref(origin)), self._ctx,

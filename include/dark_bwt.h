@@ -160,6 +160,12 @@ int dark_bwt_sort_pairs_device(dark_bwt_ctx *ctx, uint64_t *d_keys, uint32_t *d_
 int dark_bwt_verify_sa_device(dark_bwt_ctx *ctx, const uint8_t *d_text, uint64_t n, const uint32_t *d_sa,
                               uint64_t *bad_out);
 
+/* LCP profile of a block from its suffix array: m_out[r-1] = number of suffixes not unique by
+ * their first 8*2^(r-1) bytes, r = 1..*rounds_out (m_out has 64 entries), and the maximum LCP.  This is the
+ * data-defined round structure behind the algorithmic byte count B_alg = 243 n + (48 + 24 P) * sum(m_r). */
+int dark_bwt_lcp_profile_device(dark_bwt_ctx *ctx, const uint8_t *d_text, uint64_t n, const uint32_t *d_sa, uint64_t *m_out,
+                                uint32_t *rounds_out, uint64_t *max_lcp_out);
+
 /* BWT emission alone: bwt[i] = T[SA[i]-1] / origin, from a device SA. */
 int dark_bwt_emit_device(dark_bwt_ctx *ctx, const uint8_t *d_text, uint64_t n, const uint32_t *d_sa,
                          uint8_t *d_bwt_out, uint64_t *origin_out);

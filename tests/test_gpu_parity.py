@@ -431,3 +431,26 @@ def test_cpp_mirror_runs_the_reference_known_answers(torch, tmp_path):
                            "-ldark_bwt", f"-Wl,-rpath,{libdir}", "-o", str(exe)])
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), (out.returncode, out.stdout, out.stderr)
+
+
+@pytest.mark.parametrize("key", ["text:3:768771", "dna:1:1048576", "rep17:2:1048576", "mixed:4:1048576", "rep17:2:67108864",
+                                 "dna:1:268435456"])
+def test_gpu_lcp_profile_matches_the_oracle_profiler(saca, golden, torch, key):
+    """dark_bwt_lcp_profile_device: m_r, R, max LCP and B_alg from the GPU equal the oracle
+    profiler's committed values, up to the full C2 and C3 blocks."""
+    from dark_b200 import synth, _ffi
+    kind, seed, n = key.split(":")
+    n = int(n)
+    g = golden[key]["profile"]
+    t = synth.generate(kind, int(seed), n)
+    con = saca.Constructor(n, flags=_ffi.F_DEVICE_ONLY)
+    dt = torch.from_numpy(t).cuda()
+    db = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ds = torch.empty(n, dtype=torch.int32, device="cuda")
+    con.bwt_device(dt.data_ptr(), n, db.data_ptr(), ds.data_ptr())
+    p = con.lcp_profile_device(dt.data_ptr(), n, ds.data_ptr())
+    assert p["m"] == g["m"] and p["R"] == g["R"]
+    assert p["max_lcp"] == g["max_lcp"]
+    assert (p["b"], p["P"]) == (g["b"], g["P"])
+    assert abs(p["b_alg"] - g["b_alg"]) <= 1.0
+    con.close()
