@@ -454,3 +454,34 @@ def test_gpu_lcp_profile_matches_the_oracle_profiler(saca, golden, torch, key):
     assert (p["b"], p["P"]) == (g["b"], g["P"])
     assert abs(p["b_alg"] - g["b_alg"]) <= 1.0
     con.close()
+
+
+def _structured_inputs():
+    fib = [b"a", b"ab"]
+    while len(fib[-1]) < 300000:
+        fib.append(fib[-1] + fib[-2])
+    tm = bytearray(b"\x00")
+    while len(tm) < 262144:
+        tm += bytes(1 - x for x in tm)
+    rng = np.random.default_rng(99)
+    runs = np.repeat(rng.integers(0, 3, 4000).astype(np.uint8), rng.integers(1, 200, 4000))
+    return {
+        "fibonacci": fib[-1][:300007],
+        "thue_morse": bytes(tm),
+        "zeros_1M": bytes(1 << 20),
+        "ff_then_00": b"\xff" * 70000 + b"\x00" * 70001,
+        "long_runs": runs.tobytes(),
+        "period_255": bytes(range(1, 256)) * 1200,
+        "two_copies": (lambda x: x + x)(rng.integers(0, 256, 150000).astype(np.uint8).tobytes()),
+    }
+
+
+@pytest.mark.parametrize("name", ["fibonacci", "thue_morse", "zeros_1M", "ff_then_00", "long_runs", "period_255", "two_copies"])
+def test_structured_worst_cases(saca, oracle, torch, name):
+    """Highly repetitive inputs (long LCPs: many doubling rounds, giant groups, trivial digits everywhere)."""
+    t = _structured_inputs()[name]
+    bwt_o, origin_o, sa_o = oracle.bwt_forward(t, want_sa=True)
+    with saca.Constructor(len(t)) as con:
+        bwt, origin, sa = con.bwt_and_sa(t)
+        assert origin == origin_o and np.array_equal(sa, sa_o) and np.array_equal(bwt, bwt_o)
+        assert con.inverse(bwt, origin).tobytes() == t
