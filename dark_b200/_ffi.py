@@ -25,7 +25,7 @@ class Stats(ctypes.Structure):
     """dark_bwt_stats"""
     _fields_ = [
         ("n", ctypes.c_uint64), ("sigma", ctypes.c_uint32), ("bits_per_symbol", ctypes.c_uint32),
-        ("symbols_per_key", ctypes.c_uint32), ("initial_symbols", ctypes.c_uint32), ("reserved0", ctypes.c_uint32),
+        ("symbols_per_key", ctypes.c_uint32), ("initial_symbols", ctypes.c_uint32), ("pair_rounds", ctypes.c_uint32),
         ("rounds", ctypes.c_uint32), ("sort_passes", ctypes.c_uint32),
         ("kernel_launches", ctypes.c_uint32), ("active", ctypes.c_uint64 * MAX_ROUNDS),
         ("passes", ctypes.c_uint32 * MAX_ROUNDS), ("sorted_elements", ctypes.c_uint64),

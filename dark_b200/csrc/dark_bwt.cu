@@ -47,6 +47,7 @@ struct Mailbox {  // pinned host memory the device results are copied into
     float collide[kMaxPasses];
     u64 origin;
     unsigned long long bad;
+    u32 flag;  // pairs-mode detector: set when some group has three or more members
 };
 
 struct DeviceScalars {  // mirrors Mailbox on the device
@@ -501,6 +502,9 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     // survive; otherwise only the survivors' now, and per round the few that are actually read.
     bool isa_complete = true;
     int selective_rounds = 0;
+    const char* pev = getenv("DARK_BWT_PAIRS");
+    const bool use_pairs = pev ? atoi(pev) != 0 : true;
+    bool pairs_mode = false;
     const char* sev = getenv("DARK_BWT_RANK_SEARCH");
     const bool use_search = sev ? atoi(sev) != 0 : true;
     // Scatters of more than n/16 ranks into an isa[] that outgrows L2 go through the bucketed path.
@@ -540,6 +544,63 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         if (st) {
             st->active[round] = m;
             st->rounds = round;
+        }
+        // Once every remaining group is a pair the rounds switch to the pairs kernel for good (groups
+        // only ever split).  The check reads the rank list once and costs a host round trip, so it is skipped
+        // while most of the block is still active (period-17: ten rounds of giant groups).
+        if (use_pairs && !pairs_mode && (m & 1u) == 0 && (round == 1 || m <= n / 2)) {
+            ctx->mail->flag = 0;
+            u32* seen = nullptr;
+            if (int rc = next_counter(ctx, &seen)) return rc;
+            k_pairs_detect<<<(u32)ceil_div(m, 256), 256, 0, ctx->stream>>>(ctx->ranks, m, seen, &ctx->mail_dev->flag);
+            LAUNCHED();
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->mail->flag == 0) {
+                if (!isa_complete) {
+                    k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, 0u, ctx->isa);
+                    LAUNCHED();
+                    isa_complete = true;
+                }
+                pairs_mode = true;
+            }
+        }
+        if (pairs_mode) {
+            // every group is a pair: one kernel settles or keeps each pair (suffix_kernels.cuh, "pairs mode")
+            sp = span_begin(ctx, PH_RERANK);
+            constexpr int kPairThreads = 256, kPairsPerThread = 8;  // 4096 elements per tile, like the re-rank
+            const u32 tiles = (u32)ceil_div(m / 2, kPairThreads * kPairsPerThread);
+            if (tiles > ctx->scan_tiles) return ctx->fail_internal("scan tile state too small");
+            u32* counter = nullptr;
+            if (int rc = next_counter(ctx, &counter)) return rc;
+            CK(cudaMemsetAsync(ctx->scan_words, 0, sizeof(u64) * kScanWordsPerTile * tiles, ctx->stream));
+            ScanTileState ts{ctx->scan_words};
+            k_pairs_round<kPairThreads, kPairsPerThread><<<tiles, kPairThreads, 0, ctx->stream>>>(
+                ctx->ids[cur], ctx->ranks, m, n, h, ctx->isa, reinterpret_cast<uint2*>(ctx->keys[0]), sa, ctx->ids[cur ^ 1], ctx->ranks_alt, ts, counter,
+                &ctx->mail_dev->count, d_text, bwt_inline, &ctx->mail_dev->origin);
+            LAUNCHED();
+            std::swap(ctx->ranks, ctx->ranks_alt);
+            span_end(ctx, sp);
+            cur ^= 1;
+            if (st) st->pair_rounds += 1;
+            const u32 m_before = m;
+            if (int rc = fetch_count(ctx, &m)) return rc;
+            if (const u32 settled = (m_before - m) / 2) {
+                k_pairs_apply<<<(u32)ceil_div(settled, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint2*>(ctx->keys[0]), settled, ctx->isa);
+                LAUNCHED();
+            }
+            h *= 2;
+            ++round;
+            continue;
+        }
+        if (getenv("DARK_BWT_GROUP_STATS")) {  // debug: group-size statistics of the active list
+            CK(cudaMemsetAsync(ctx->bucket_hist, 0, 8, ctx->stream));
+            k_group_stats<<<(u32)ceil_div(m, 256), 256, 0, ctx->stream>>>(ctx->ranks, m, ctx->bucket_hist);
+            LAUNCHED();
+            u32 gs[2] = {0, 0};
+            CK(cudaMemcpyAsync(gs, ctx->bucket_hist, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            fprintf(stderr, "[dark_bwt] round %d: h=%llu active=%u groups=%u max_group=%u%s\n", round, (unsigned long long)h, m, gs[1],
+                    gs[0], gs[0] >= 4096 ? "+" : "");
         }
         sp = span_begin(ctx, PH_KEYBUILD);
         CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));

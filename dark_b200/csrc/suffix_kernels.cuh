@@ -1053,6 +1053,150 @@ k_lcp_buckets(const u32* __restrict__ lcp, u32 n, unsigned long long* __restrict
     if (threadIdx.x == 0) atomicMax(max_out, s_max);
 }
 
+// ---- pairs mode -----------------------------------------------------------------------------------
+// Long repeats leave an active list made of PAIRS only (two suffixes tied over a long common prefix:
+// the mixed 256 MiB block has nothing but pairs from round 4 on, for 8 more rounds).  Sorting a
+// group of two needs no sort: one kernel per round gathers both second ranks, settles the pair when they
+// differ and keeps it otherwise.  Replaces key build + 7 radix passes + re-rank for those rounds.
+__global__ void __launch_bounds__(256) k_pairs_detect(const u32* __restrict__ ranks, u32 m, u32* __restrict__ seen, u32* __restrict__ not_pairs) {
+    const u64 p = (u64)blockIdx.x * 256 + threadIdx.x;
+    const int big = p + 2 < m && ranks[p] == ranks[p + 2];  // a group of three or more
+    // `not_pairs` lives in mapped host memory: exactly one thread of the grid writes it
+    if (__syncthreads_or(big) && threadIdx.x == 0 && ld_relaxed(seen) == 0 && atomicExch(seen, 1u) == 0) *not_pairs = 1;
+}
+
+__global__ void __launch_bounds__(256) k_pairs_apply(const uint2* __restrict__ pending, u32 count, u32* __restrict__ isa) {
+    const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (i < count) {
+        const uint2 e = pending[i];
+        isa[e.x] = e.y;
+    }
+}
+
+template <int THREADS, int PPT>  // PPT pairs per thread
+__global__ void __launch_bounds__(THREADS)
+k_pairs_round(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m, u32 n, u64 h, const u32* __restrict__ isa_ro,
+              uint2* __restrict__ pending, u32* __restrict__ sa, u32* __restrict__ out_ids, u32* __restrict__ out_ranks,
+              ScanTileState ts, u32* __restrict__ tile_counter, u32* __restrict__ out_count, const u8* __restrict__ text,
+              u8* __restrict__ bwt_inline, u64* __restrict__ origin) {
+    constexpr int TILE_PAIRS = THREADS * PPT;
+    constexpr int WARPS = THREADS / 32;
+    __shared__ u32 s_warp[WARPS];
+    __shared__ u32 s_excl, s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u32 npairs = m >> 1;
+    const u64 q0 = (u64)tile * TILE_PAIRS + (u64)tid * PPT;  // first pair of this thread
+
+    u32 a[PPT], b[PPT], r[PPT], ra[PPT], rb[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const u64 q = q0 + k;
+        if (q < npairs) {
+            const uint2 id2 = *reinterpret_cast<const uint2*>(ids + 2 * q);
+            a[k] = id2.x;
+            b[k] = id2.y;
+            r[k] = ranks[2 * q];
+        } else {
+            a[k] = b[k] = r[k] = 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const u64 pa = (u64)a[k] + h, pb = (u64)b[k] + h;
+        ra[k] = (q0 + k < npairs && pa < n) ? __ldg(isa_ro + pa) + 1u : 0u;
+        rb[k] = (q0 + k < npairs && pb < n) ? __ldg(isa_ro + pb) + 1u : 0u;
+    }
+    u32 tied = 0;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k)
+        if (q0 + k < npairs && ra[k] == rb[k]) tied |= 1u << k;
+    const u32 mine = __popc(tied);
+
+    // exclusive scan of the surviving pairs: warp, CTA, then a 32-tile look-back window on one word
+    u32 incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    u32 wprefix = 0;
+    for (int w = 0; w < warp; ++w) wprefix += s_warp[w];
+    if (warp == 0) {
+        u32 total = 0;
+        for (int w = 0; w < WARPS; ++w) total += s_warp[w];
+        u64* word = ts.words + (size_t)tile * kScanWordsPerTile + 2;
+        u32 excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st_relaxed(word, scan_pack(2u, total));
+        } else {
+            if (lane == 0) st_relaxed(word, scan_pack(1u, total));
+            int base = (int)tile - 1;
+            for (;;) {
+                const int t = base - lane;
+                u64 w2 = scan_pack(2u, 0u);
+                if (t >= 0) {
+                    const u64* theirs = ts.words + (size_t)t * kScanWordsPerTile + 2;
+                    do { w2 = ld_relaxed(theirs); } while ((w2 >> 62) == 0);
+                }
+                const u32 im = __ballot_sync(0xffffffffu, (w2 >> 62) == 2);
+                const int first = im ? (__ffs(im) - 1) : 31;
+                excl += __reduce_add_sync(0xffffffffu, lane <= first ? (u32)w2 : 0u);
+                if (im) break;
+                base -= 32;
+            }
+            if (lane == 0) st_relaxed(word, scan_pack(2u, excl + total));
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if ((u64)(tile + 1) * TILE_PAIRS >= npairs) *out_count = 2u * (excl + total);  // survivors (elements)
+        }
+    }
+    __syncthreads();
+    u32 slot = s_excl + wprefix + incl - mine;  // index of this thread's first surviving pair
+
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        if (q0 + k >= npairs) continue;
+        if ((tied >> k) & 1u) {  // still tied: the pair survives with its rank
+            *reinterpret_cast<uint2*>(out_ids + 2 * (u64)slot) = make_uint2(a[k], b[k]);
+            *reinterpret_cast<uint2*>(out_ranks + 2 * (u64)slot) = make_uint2(r[k], r[k]);
+            ++slot;
+        } else {  // settled: the smaller second rank takes slot r, the other r+1
+            const bool a_first = ra[k] < rb[k];
+            const u32 lo = a_first ? a[k] : b[k], hi = a_first ? b[k] : a[k];
+            sa[r[k]] = lo;
+            sa[r[k] + 1] = hi;
+            // lo keeps rank r; hi's new rank is applied after the kernel (k_pairs_apply) so that every
+            // gather of this round sees the ranks of the previous round: the round count stays canonical
+            pending[q0 + k - slot] = make_uint2(hi, r[k] + 1);
+            if (bwt_inline != nullptr) {
+                bwt_inline[r[k]] = __ldg(text + (lo == 0 ? n - 1 : lo - 1));
+                bwt_inline[r[k] + 1] = __ldg(text + (hi == 0 ? n - 1 : hi - 1));
+                if (lo == 0) *origin = r[k];
+                if (hi == 0) *origin = (u64)r[k] + 1;
+            }
+        }
+    }
+}
+
+// Debug statistic (DARK_BWT_GROUP_STATS=1): largest group of the active list (capped at 4096) and the
+// number of groups, from the rank list (equal rank = same group, groups are contiguous).
+__global__ void __launch_bounds__(256) k_group_stats(const u32* __restrict__ ranks, u32 m, u32* __restrict__ out /* [0]=max size, [1]=groups */) {
+    const u64 p = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (p >= m) return;
+    const u32 r = ranks[p];
+    if (p > 0 && ranks[p - 1] == r) return;  // not a head
+    u32 len = 1;
+    while (p + len < m && len < 4096 && ranks[p + len] == r) ++len;
+    atomicMax(out, len);
+    atomicAdd(out + 1, 1u);
+}
+
 // ---- verification (independent of the construction kernels) ------------------------------------
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_verify_scatter(const u32* __restrict__ sa, u32 n, u32* __restrict__ isa, unsigned long long* bad) {

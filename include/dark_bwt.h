@@ -73,7 +73,7 @@ typedef struct dark_bwt_stats {
     uint32_t bits_per_symbol; /* s                                                        */
     uint32_t symbols_per_key; /* K: symbols packed into the initial 64-bit key            */
     uint32_t initial_symbols; /* K0 <= K: whole symbols the (pruned) initial sort ordered */
-    uint32_t reserved0;
+    uint32_t pair_rounds;     /* rounds handled by the pairs kernel (every group was a pair)  */
     uint32_t rounds;          /* prefix-doubling rounds after the initial sort            */
     uint32_t sort_passes;     /* radix-pass kernel launches, all rounds                   */
     uint32_t kernel_launches; /* every kernel this call launched                          */

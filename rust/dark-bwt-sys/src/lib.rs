@@ -16,7 +16,7 @@ pub struct dark_bwt_stats {
     pub bits_per_symbol: u32,
     pub symbols_per_key: u32,
     pub initial_symbols: u32,
-    pub reserved0: u32,
+    pub pair_rounds: u32,
     pub rounds: u32,
     pub sort_passes: u32,
     pub kernel_launches: u32,

@@ -168,6 +168,7 @@ FORCED_PATHS = [
     ({"DARK_BWT_SORT_VARIANT": "5"}, "dna", 1, 700001),
     ({"DARK_BWT_TILE_BY_BLOCKIDX": "1"}, "mixed", 9, 900001),
     ({"DARK_BWT_RANK_SEARCH": "0"}, "dna", 6, 1500003),              # selective rank fill (bitmap + SA sweep) instead of the search
+    ({"DARK_BWT_PAIRS": "0"}, "mixed", 4, 1300001),                  # late rounds WITHOUT the pairs kernel
     ({"DARK_BWT_INLINE_EMIT": "0"}, "dna", 3, 1200007),              # pruned initial sort WITHOUT inline emission
     ({"DARK_BWT_INLINE_EMIT": "0", "DARK_BWT_EMIT_WINDOW_MB": "1"}, "dna", 4, 3000001),        # tiles ordered by blockIdx instead of the claim counter
 ]
@@ -485,3 +486,33 @@ def test_structured_worst_cases(saca, oracle, torch, name):
         bwt, origin, sa = con.bwt_and_sa(t)
         assert origin == origin_o and np.array_equal(sa, sa_o) and np.array_equal(bwt, bwt_o)
         assert con.inverse(bwt, origin).tobytes() == t
+
+
+# ---- pairs mode (late rounds in which every group is a pair) -----------------------------------
+def _pairs_inputs():
+    rng = np.random.default_rng(7)
+    dna = rng.integers(0, 4, 2_000_003).astype(np.uint8) + 65
+    planted = dna.copy()
+    planted[1_200_000:1_200_000 + 5000] = planted[100_000:100_000 + 5000]      # one long repeat in random DNA
+    nested = rng.integers(0, 256, 600_000).astype(np.uint8)
+    nested[400_000:400_000 + 70_000] = nested[10_000:10_000 + 70_000]            # a pair of long copies ...
+    nested[500_000:500_000 + 300] = nested[20_000:20_000 + 300]                  # ... and a triple inside it
+    two = rng.integers(0, 256, 150_001).astype(np.uint8)
+    return {"planted_dna": planted, "nested_repeats": nested, "two_copies_odd": np.concatenate([two, two]),
+            "tail_repeat": np.concatenate([rng.integers(0, 256, 300_000).astype(np.uint8)] * 1 + [np.arange(40_000, dtype=np.uint8)])}
+
+
+@pytest.mark.parametrize("name", ["planted_dna", "nested_repeats", "two_copies_odd", "tail_repeat"])
+def test_pairs_mode_rounds(saca, oracle, torch, name):
+    """Inputs whose late rounds hold nothing but pairs: the pairs kernel must take over (stats.pair_rounds > 0),
+    leave the per-round active counts canonical and produce the oracle's bytes; both alphabet modes."""
+    t = _pairs_inputs()[name]
+    bwt_o, origin_o, sa_o = oracle.bwt_forward(t, want_sa=True)
+    (bwt, origin, sa, st), (bwt2, origin2, sa2, st2) = run_both_modes(saca, t)
+    assert origin == origin_o == origin2
+    assert np.array_equal(sa, sa_o) and np.array_equal(sa2, sa_o)
+    assert np.array_equal(bwt, bwt_o) and np.array_equal(bwt2, bwt_o)
+    if name != "tail_repeat":
+        assert st["pair_rounds"] > 0 and st2["pair_rounds"] > 0, (st["pair_rounds"], st2["pair_rounds"])
+    prof = oracle.profile(t, sa_o)
+    assert st2["active"][1:1 + len(prof["m"])] == prof["m"], (st2["active"], prof["m"])
