@@ -172,11 +172,11 @@ int next_counter(dark_bwt_ctx* ctx, u32** out) {
 
 // Tuning variants of the radix pass (threads, items per thread, min CTAs per SM).  The default is
 // chosen from measurements (profiles/); DARK_BWT_SORT_VARIANT=<i> selects another one for sweeps.
-template <int THREADS, int ITEMS, int MINBLOCKS, int ILP, typename StatusT, bool ALIGNED>
+template <int THREADS, int ITEMS, int MINBLOCKS, int ILP, typename StatusT, bool ALIGNED, bool GEN = false>
 int launch_pass_kernel(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
-                       const u32* digit_base, u32* counter, u32 tiles, const u8* prev_text, u32 n_text) {
+                       const u32* digit_base, u32* counter, u32 tiles, const u8* prev_text, u32 n_text, KeyGen gen = KeyGen()) {
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
-    auto kern = k_onesweep_pass<THREADS, ITEMS, MINBLOCKS, ILP, StatusT, ALIGNED>;
+    auto kern = k_onesweep_pass<THREADS, ITEMS, MINBLOCKS, ILP, StatusT, ALIGNED, GEN>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));  // per device
     static const bool by_block_index = getenv("DARK_BWT_TILE_BY_BLOCKIDX") != nullptr;
     const char* ke = getenv("DARK_BWT_PASS_KNOCKOUT");  // measurement only: skip phases (1 look-back, 2 ranking, 4 stores)
@@ -184,14 +184,14 @@ int launch_pass_kernel(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* k
     // persistent grid: as many CTAs as stay resident (SMs x MINBLOCKS), each claiming tiles until none are left
     const u32 grid = by_block_index ? tiles : std::min<u32>(tiles, (u32)ctx->num_sms * MINBLOCKS);
     kern<<<grid, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base, (StatusT*)ctx->sort_status,
-                                                        by_block_index ? nullptr : counter, ctx->pass_trace, prev_text, n_text, knock);
+                                                        by_block_index ? nullptr : counter, ctx->pass_trace, prev_text, n_text, knock, gen);
     LAUNCHED();
     return 0;
 }
 
 template <int THREADS, int ITEMS, int MINBLOCKS, int ILP>
 int launch_pass_variant(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
-                        const u32* digit_base, u32* counter, bool wide, const u8* prev_text, u32 n_text) {
+                        const u32* digit_base, u32* counter, bool wide, const u8* prev_text, u32 n_text, const KeyGen* gen = nullptr) {
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
     const u32 tiles = (u32)ceil_div(m, Smem::kTile);
     const size_t bytes = (size_t)tiles * kRadix * (wide ? sizeof(u64) : sizeof(u32));
@@ -199,6 +199,14 @@ int launch_pass_variant(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* 
     CK(cudaMemsetAsync(ctx->sort_status, 0, bytes, ctx->stream));
     const bool aligned = (shift & 7) == 0;  // always true for the suffix sorter; the public sort may differ
 #define LP(ST, AL) launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, ILP, ST, AL>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, tiles, prev_text, n_text)
+    if (gen != nullptr) {  // keys built from the text inside the pass (default tiling, byte-aligned digits only)
+        if (!aligned) return ctx->fail_internal("key-generating pass needs a byte-aligned digit");
+        if (wide)
+            return launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, ILP, u64, true, true>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter,
+                                                                                       tiles, prev_text, n_text, *gen);
+        return launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, ILP, u32, true, true>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter,
+                                                                                   tiles, prev_text, n_text, *gen);
+    }
     if (!aligned) return wide ? LP(u64, false) : LP(u32, false);
     return wide ? LP(u64, true) : LP(u32, true);
 #undef LP
@@ -208,7 +216,7 @@ constexpr int kDefaultSortVariant = 1;  // 256 threads x 16 items, 3 CTAs/SM: be
 
 // One onesweep pass over m pairs: buffers[cur] -> buffers[cur^1].
 int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift,
-                const u32* digit_base, const u8* prev_text = nullptr, u32 n_text = 0) {
+                const u32* digit_base, const u8* prev_text = nullptr, u32 n_text = 0, const KeyGen* gen = nullptr) {
     u32* counter = nullptr;
     if (int rc = next_counter(ctx, &counter)) return rc;
     // 32-bit status words hold prefixes below 2^30; larger sorts (2 GiB blocks) use 64-bit words.
@@ -216,6 +224,7 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
     const bool wide = !(m < (1u << 30)) || getenv("DARK_BWT_FORCE_U64_STATUS") != nullptr;
     const char* ev = getenv("DARK_BWT_SORT_VARIANT");
     const int variant = ev ? atoi(ev) : kDefaultSortVariant;
+    if (gen != nullptr) return launch_pass_variant<256, 16, 3, 2>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, n_text, gen);
 #define V(T, I, B, L) return launch_pass_variant<T, I, B, L>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, n_text)
     switch (variant) {
         case 0: V(256, 16, 2, 2);
@@ -241,7 +250,7 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
 // *first_pass_out = index of the lowest digit that was sorted.
 int run_sort(dark_bwt_ctx* ctx, u64* const keys[2], u32* const vals[2], int cur, u32 m, int begin_bit, int num_passes,
              int* cur_out, dark_bwt_stats* st, int round, bool prune = false, int* first_pass_out = nullptr,
-             const u8* patch_text = nullptr, bool* patched_out = nullptr) {
+             const u8* patch_text = nullptr, bool* patched_out = nullptr, const KeyGen* gen = nullptr, bool* gen_used_out = nullptr) {
     // Scalar results (flags, counts, origin) are written by the kernels directly into mapped pinned host
     // memory and read after a stream sync.  A cudaMemcpy D2H would queue on the copy engine behind the
     // 256 MB block transfers of the pipelined batch entry (measured: +5 ms per block).
@@ -271,8 +280,12 @@ int run_sort(dark_bwt_ctx* ctx, u64* const keys[2], u32* const vals[2], int cur,
     for (int p = first; p < num_passes; ++p) {
         if (ctx->mail->trivial[p]) continue;  // every key has the same digit: the pass is the identity
         if (int rc = launch_pass(ctx, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], m, begin_bit + p * kRadixBits,
-                                 ctx->hist + p * kRadix, patch, m))
+                                 ctx->hist + p * kRadix, patch, m, gen))
             return rc;
+        if (gen) {  // only the first pass that runs builds its input; the later ones read what it wrote
+            if (gen_used_out) *gen_used_out = true;
+            gen = nullptr;
+        }
         if (patch) {
             if (patched_out) *patched_out = true;
             patch = nullptr;
@@ -446,11 +459,28 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     }
 
     // ---- round 0: keys of K symbols, ids descending
-    {
+    // Fused initial keys (s in {1,2,4,8}): the key builder only counts digits; the first radix pass that runs
+    // rebuilds the keys from the text (radix_sort.cuh, GEN).  DARK_BWT_FUSED_INIT=0 materialises them instead.
+    const char* fev = getenv("DARK_BWT_FUSED_INIT");
+    const bool packed_s = s_bits == 1 || s_bits == 2 || s_bits == 4 || s_bits == 8;
+    const bool fuse_init = packed_s && (fev ? atoi(fev) != 0 : true) && getenv("DARK_BWT_SORT_VARIANT") == nullptr;
+    const char* gev = getenv("DARK_BWT_GRAM_HIST");
+    const bool gram_hist = packed_s && (gev ? atoi(gev) != 0 : true);  // histograms from the text's q-grams (suffix_kernels.cuh)
+    const int lg_s = s_bits == 1 ? 0 : s_bits == 2 ? 1 : s_bits == 4 ? 2 : 3;
+    auto init_keys = [&](bool write, bool hist) -> int {
         const u32 blocks = (u32)std::min<u64>(ceil_div(n, kInitThreads * kInitItems), (u64)ctx->num_sms * 8);
-#define INIT_PACKED(S)                                                                                            \
-    k_init_keys_packed<kInitThreads, kInitItems, S><<<blocks, kInitThreads, 0, ctx->stream>>>(d_text, n, ctx->lut, \
-                                                                                              ctx->keys[0], ctx->ids[0], ctx->hist)
+#define INIT_PACKED(S)                                                                                                              \
+    do {                                                                                                                            \
+        if (write && hist)                                                                                                          \
+            k_init_keys_packed<kInitThreads, kInitItems, S, true, true><<<blocks, kInitThreads, 0, ctx->stream>>>(                  \
+                d_text, n, ctx->lut, ctx->keys[0], ctx->ids[0], ctx->hist);                                                         \
+        else if (write)                                                                                                             \
+            k_init_keys_packed<kInitThreads, kInitItems, S, true, false><<<blocks, kInitThreads, 0, ctx->stream>>>(                 \
+                d_text, n, ctx->lut, ctx->keys[0], ctx->ids[0], ctx->hist);                                                         \
+        else                                                                                                                        \
+            k_init_keys_packed<kInitThreads, kInitItems, S, false, true><<<blocks, kInitThreads, 0, ctx->stream>>>(d_text, n, ctx->lut, \
+                                                                                                               nullptr, nullptr, ctx->hist); \
+    } while (0)
         switch (s_bits) {
             case 1: INIT_PACKED(1); break;
             case 2: INIT_PACKED(2); break;
@@ -462,6 +492,36 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         }
 #undef INIT_PACKED
         LAUNCHED();
+        return 0;
+    };
+    if (gram_hist) {
+        u32* gram = ctx->bucket_hist;  // 256 counters, free until the first rank scatter
+        CK(cudaMemsetAsync(gram, 0, sizeof(u32) * kRadix, ctx->stream));
+        const u32 blocks = (u32)std::min<u64>(ceil_div(n, 256 * 16), (u64)ctx->num_sms * 8);
+        switch (s_bits) {
+            case 1: k_gram_hist<256, 1><<<blocks, 256, 0, ctx->stream>>>(d_text, n, ctx->lut, gram); break;
+            case 2: k_gram_hist<256, 2><<<blocks, 256, 0, ctx->stream>>>(d_text, n, ctx->lut, gram); break;
+            case 4: k_gram_hist<256, 4><<<blocks, 256, 0, ctx->stream>>>(d_text, n, ctx->lut, gram); break;
+            default: k_gram_hist<256, 8><<<blocks, 256, 0, ctx->stream>>>(d_text, n, ctx->lut, gram); break;
+        }
+        LAUNCHED();
+        k_gram_expand<<<1, kRadix, 0, ctx->stream>>>(d_text, n, ctx->lut, lg_s, gram, ctx->hist);
+        LAUNCHED();
+        if (getenv("DARK_BWT_CHECK_HIST")) {  // test hook: compare with the histogram counted key by key
+            std::vector<u32> a(kMaxPasses * kRadix), b(kMaxPasses * kRadix);
+            CK(cudaMemcpyAsync(a.data(), ctx->hist, a.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
+            if (int rc = init_keys(false, true)) return rc;
+            CK(cudaMemcpyAsync(b.data(), ctx->hist, b.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (a != b) return ctx->fail_internal("q-gram histogram differs from the per-key histogram");
+            CK(cudaMemcpyAsync(ctx->hist, a.data(), a.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        if (!fuse_init)
+            if (int rc = init_keys(true, false)) return rc;
+    } else {
+        if (int rc = init_keys(!fuse_init, true)) return rc;
     }
     span_end(ctx, sp);
 
@@ -473,9 +533,19 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     const char* iev = getenv("DARK_BWT_INLINE_EMIT");
     const bool want_inline = iev ? atoi(iev) != 0 : true;
     bool emit_inline = false;
+    KeyGen gen;
+    gen.text = d_text;
+    gen.lut = ctx->lut;
+    gen.n = n;
+    gen.lg_s = lg_s;
+    bool gen_used = false;
     if (int rc = run_sort(ctx, ctx->keys, ctx->ids, cur, n, 0, passes0, &cur, st, 0, /*prune=*/!no_pack, &first_pass,
-                          want_inline ? d_text : nullptr, &emit_inline))
+                          want_inline ? d_text : nullptr, &emit_inline, fuse_init ? &gen : nullptr, &gen_used))
         return rc;
+    if (fuse_init && !gen_used) {  // every digit was trivial (one-symbol text): no pass ran, the re-rank still wants the keys
+        if (int rc = init_keys(true, false)) return rc;
+        cur = 0;
+    }
     span_end(ctx, sp);
     u8* bwt_inline = emit_inline ? d_bwt : nullptr;
     // The sort covered the key bits above `drop`: K0 whole leading symbols are known equal inside a

@@ -216,6 +216,17 @@ struct DigitLookback {
     }
 };
 
+// GEN (first pass of the suffix sorter's round 0): the (key, id) pairs are not read from memory but
+// built from the text on the fly — element j is suffix id = n-1-j, its key the first 64/s symbols as dense
+// s-bit codes (exactly what k_init_keys_packed would have written, suffix_kernels.cuh).  Saves the 12 B per
+// suffix the key builder would write and the 12 B this pass would read back.
+struct KeyGen {
+    const u8* text;
+    const u8* lut;  // byte -> dense code
+    u32 n;
+    int lg_s;       // log2(bits per symbol): s in {1, 2, 4, 8}
+};
+
 // The body of one tile.  FULL = all THREADS*ITEMS slots hold a pair (every tile but the last):
 // no validity predicates anywhere on that path.
 // Tried and rejected (measurements in profiles/r1_pass_trace_v4.md): publishing the aggregate from a
@@ -223,12 +234,13 @@ struct DigitLookback {
 // pairs instead of 1.07: the prefix still appears only after the ranking, so walks get longer), and a
 // dedicated scan warp doing the look-back beside the ranking warps (2.1 ms: one warp cannot keep enough
 // status loads in flight).
-template <int THREADS, int ITEMS, int ILP, typename StatusT, bool ALIGNED, bool FULL>
+template <int THREADS, int ITEMS, int ILP, typename StatusT, bool ALIGNED, bool FULL, bool GEN>
 __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, const u64* __restrict__ keys_in,
                                               const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
                                               u32* __restrict__ vals_out, const u32 tile, const u32 nvalid, const int shift,
                                               const u32* __restrict__ digit_base, StatusT* __restrict__ status,
-                                              long long* __restrict__ trace, const u8* __restrict__ prev_text, const u32 n_text, const u32 knock) {
+                                              long long* __restrict__ trace, const u8* __restrict__ prev_text, const u32 n_text, const u32 knock,
+                                              const KeyGen gen) {
     // knock != 0 (tools/sort_bench.py KNOCKOUT only): phases are skipped to measure what they cost; output is garbage
     // trace != nullptr (tools/pass_trace.py only): thread 0 stamps clock64() at the phase boundaries
 #define DARK_STAMP(i) do { if (trace && threadIdx.x == 0) trace[(size_t)tile * 12 + (i)] = clock64(); } while (0)
@@ -242,10 +254,48 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
     // warp-striped arrangement: element (warp, k, lane) has tile-local index warp*32*ITEMS + k*32 + lane,
     // so every load instruction of a warp covers 32 consecutive pairs and rank order == index order.
     const u32 local0 = warp * (32 * ITEMS) + lane;
-    const u64* kp = keys_in + tile_base + local0;
     u64 key[ITEMS];
+    if (GEN) {
+        // the tile's symbol codes, packed MSB-first into 32-bit words (s.keys is free until the re-order);
+        // a key is a 64-bit window of that bit stream
+        u32* words = reinterpret_cast<u32*>(s.keys);
+        const int lg_s = gen.lg_s, sbits = 1 << lg_s, spw = 32 >> lg_s;
+        const u64 i_lo = (u64)gen.n - tile_base - nvalid;  // lowest text position of this tile
+        const u32 nwords = ((u32)(TILE + (64 >> lg_s)) >> (5 - lg_s)) + 3;
+        for (u32 w = tid; w < nwords; w += THREADS) {
+            u32 word = 0;
+            const u64 pos0 = i_lo + ((u64)w << (5 - lg_s));
+            for (int c = 0; c < spw; c += 4) {
+                u32 code[4];
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) key[k] = (FULL || local0 + k * 32 < nvalid) ? ld_stream(kp + k * 32) : ~0ull;
+                for (int e = 0; e < 4; ++e) code[e] = pos0 + c + e < gen.n ? (u32)__ldg(gen.text + pos0 + c + e) : 0x100u;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) code[e] = code[e] < 0x100u ? (u32)__ldg(gen.lut + code[e]) : 0u;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) word = (word << sbits) | code[e];
+            }
+            words[w] = word;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const u32 jl = local0 + k * 32;
+            key[k] = ~0ull;
+            if (FULL || jl < nvalid) {
+                const u32 x = nvalid - 1 - jl;
+                const u32 bit = x << lg_s;
+                const u32 wi = bit >> 5, sh = bit & 31;
+                const u32 w0 = words[wi], w1 = words[wi + 1], w2 = words[wi + 2];
+                key[k] = ((u64)__funnelshift_l(w1, w0, sh) << 32) | __funnelshift_l(w2, w1, sh);
+                s.raw_vals[jl] = (u32)(i_lo + x);
+            }
+        }
+        // (the words are dead once every thread has passed the barrier that follows the ranking loop)
+    } else {
+        const u64* kp = keys_in + tile_base + local0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) key[k] = (FULL || local0 + k * 32 < nvalid) ? ld_stream(kp + k * 32) : ~0ull;
+    }
     if (prev_text != nullptr) {
         // First pass of a pruned initial sort (the low key byte is not sorted): element j is still suffix
         // n-1-j, so its BWT byte T[id-1] is a contiguous read; it rides in the low key byte from here on
@@ -261,7 +311,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
     }
     // The values go straight to shared memory with cp.async (no registers held across the ranking
     // loop, latency hidden behind it); each thread later reads back exactly the words it copied.
-    {
+    if (!GEN) {
         const u32* vp = vals_in + tile_base + local0;
         const u32 dst = smem_addr(&s.raw_vals[local0]);
 #pragma unroll
@@ -390,12 +440,12 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
 #undef DARK_STAMP
 }
 
-template <int THREADS, int ITEMS, int MINBLOCKS, int ILP, typename StatusT, bool ALIGNED>
+template <int THREADS, int ITEMS, int MINBLOCKS, int ILP, typename StatusT, bool ALIGNED, bool GEN = false>
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
                 u32* __restrict__ vals_out, u32 m, int shift, const u32* __restrict__ digit_base,
                 StatusT* __restrict__ status, u32* __restrict__ tile_counter, long long* __restrict__ trace,
-                const u8* __restrict__ prev_text, u32 n_text, u32 knock) {
+                const u8* __restrict__ prev_text, u32 n_text, u32 knock, KeyGen gen) {
     static_assert(THREADS >= kRadix && THREADS % 32 == 0, "one thread per digit is assumed");
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
     constexpr int TILE = Smem::kTile;
@@ -429,11 +479,11 @@ k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in
         }
         const u32 nvalid = (u32)min((u64)TILE, (u64)m - (u64)tile * TILE);
         if (nvalid == TILE)
-            onesweep_tile<THREADS, ITEMS, ILP, StatusT, ALIGNED, true>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid,
-                                                                              shift, digit_base, status, trace, prev_text, n_text, knock);
+            onesweep_tile<THREADS, ITEMS, ILP, StatusT, ALIGNED, true, GEN>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid,
+                                                                            shift, digit_base, status, trace, prev_text, n_text, knock, gen);
         else
-            onesweep_tile<THREADS, ITEMS, ILP, StatusT, ALIGNED, false>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid,
-                                                                               shift, digit_base, status, trace, prev_text, n_text, knock);
+            onesweep_tile<THREADS, ITEMS, ILP, StatusT, ALIGNED, false, GEN>(s, keys_in, vals_in, keys_out, vals_out, tile, nvalid,
+                                                                             shift, digit_base, status, trace, prev_text, n_text, knock, gen);
         if (tile_counter == nullptr) break;
         __syncthreads();  // the scatter has read the shared tile: it may be overwritten now
     }

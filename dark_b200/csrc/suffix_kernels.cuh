@@ -120,7 +120,9 @@ k_init_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ lut, int 
 // packed MSB-first into 32-bit words in shared memory; a key is then a 64-bit window of that bit
 // stream (3 LDS + 2 funnel shifts instead of K byte loads — the byte loop made the first version
 // of this kernel issue-bound at K = 32, profiles/r1_ncu_c2_v1.md).
-template <int THREADS, int ITEMS, int S>
+// WRITE = false: digit histogram only (the keys are rebuilt inside the first radix pass, radix_sort.cuh GEN).
+// HIST = false: keys only (the histogram came from k_gram_hist).
+template <int THREADS, int ITEMS, int S, bool WRITE, bool HIST>
 __global__ void __launch_bounds__(THREADS)
 k_init_keys_packed(const u8* __restrict__ text, u32 n, const u8* __restrict__ lut, u64* __restrict__ keys_out,
                    u32* __restrict__ ids_out, u32* __restrict__ g_hist) {
@@ -164,14 +166,90 @@ k_init_keys_packed(const u8* __restrict__ text, u32 n, const u8* __restrict__ lu
                 const u32 hi = __funnelshift_l(w1, w0, sh);
                 const u32 lo = __funnelshift_l(w2, w1, sh);
                 const u64 key = ((u64)hi << 32) | lo;
-                keys_out[jb + jl] = key;
-                ids_out[jb + jl] = (u32)(i_lo + x);
-                hist_add_key(s_hist, key, 0, kMaxPasses);
+                if (WRITE) {
+                    keys_out[jb + jl] = key;
+                    ids_out[jb + jl] = (u32)(i_lo + x);
+                }
+                if (HIST) hist_add_key(s_hist, key, 0, kMaxPasses);
             }
         }
         __syncthreads();
     }
-    hist_flush(s_hist, g_hist, kMaxPasses, tid, THREADS);
+    if (HIST) hist_flush(s_hist, g_hist, kMaxPasses, tid, THREADS);
+}
+
+// Digit histograms of the initial keys without building a key.  For s in {1,2,4,8} a radix digit is a whole
+// number Q = 8/s of symbols, so digit t (from the top) of the key of suffix i is the Q-gram at text position
+// i + tQ (zero-padded past the end): all eight histograms are the ONE Q-gram histogram G of the text, minus
+// the grams of the first tQ positions, plus tQ padding grams.  One shared-memory atomic per text byte
+// instead of eight per key (the fused count in the key builder was bank-conflict bound at 0.95 ms per 2^28).
+template <int THREADS, int S>
+__global__ void __launch_bounds__(THREADS)
+k_gram_hist(const u8* __restrict__ text, u32 n, const u8* __restrict__ lut, u32* __restrict__ g_gram) {
+    constexpr int Q = 8 / S;
+    constexpr int WARPS = THREADS / 32;
+    constexpr int PER = 16;  // text positions per thread and step
+    __shared__ u32 s_h[WARPS][kRadix];
+    __shared__ u8 s_lut[256];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < WARPS * kRadix; i += THREADS) (&s_h[0][0])[i] = 0;
+    for (int i = tid; i < 256; i += THREADS) s_lut[i] = lut[i];
+    __syncthreads();
+    const bool vec = (((uintptr_t)text) & 15) == 0;
+    for (u64 base = (u64)blockIdx.x * (THREADS * PER); base < n; base += (u64)gridDim.x * (THREADS * PER)) {
+        const u64 i0 = base + (u64)tid * PER;
+        if (i0 >= n) continue;
+        u32 code[PER + Q - 1];
+        if (vec && i0 + PER <= n) {
+            const uint4 v = *reinterpret_cast<const uint4*>(text + i0);
+            const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < PER; ++e) code[e] = s_lut[(w[e >> 2] >> (8 * (e & 3))) & 0xFFu];
+        } else {
+#pragma unroll
+            for (int e = 0; e < PER; ++e) code[e] = i0 + e < n ? (u32)s_lut[text[i0 + e]] : 0u;
+        }
+#pragma unroll
+        for (int e = PER; e < PER + Q - 1; ++e) code[e] = i0 + e < n ? (u32)s_lut[text[i0 + e]] : 0u;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            u32 gram = 0;
+#pragma unroll
+            for (int c = 0; c < Q; ++c) gram = (gram << S) | code[e + c];
+            if (i0 + e < n) atomicAdd(&s_h[warp][gram & 0xFFu], 1u);
+        }
+    }
+    __syncthreads();
+    for (int d = tid; d < kRadix; d += THREADS) {
+        u32 c = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) c += s_h[w][d];
+        if (c) atomicAdd(&g_gram[d], c);
+    }
+}
+
+// G -> the eight digit histograms (row p = digit at bit 8p, i.e. t = 7-p from the top); one CTA of 256 threads.
+__global__ void __launch_bounds__(kRadix) k_gram_expand(const u8* __restrict__ text, u32 n, const u8* __restrict__ lut, int lg_s,
+                                                        const u32* __restrict__ g_gram, u32* __restrict__ g_hist) {
+    __shared__ u32 s_code[72];
+    __shared__ u32 s_gram[64];
+    const int v = threadIdx.x;
+    const int S = 1 << lg_s, Q = 8 >> lg_s;
+    if (v < 72) s_code[v] = (u32)v < n ? (u32)lut[text[v]] : 0u;
+    __syncthreads();
+    if (v < 64) {
+        u32 gram = 0;
+        for (int c = 0; c < Q; ++c) gram = (gram << S) | s_code[v + c];
+        s_gram[v] = gram & 0xFFu;
+    }
+    __syncthreads();
+    const u32 G = g_gram[v];
+    for (int t = 0; t < kMaxPasses; ++t) {
+        const u32 c = min((u32)(t * Q), n);  // leading positions that digit t never sees = padding grams it sees instead
+        u32 lead = 0;
+        for (u32 j = 0; j < c; ++j) lead += s_gram[j] == (u32)v ? 1u : 0u;
+        g_hist[(kMaxPasses - 1 - t) * kRadix + v] = G - lead + (v == 0 ? c : 0u);
+    }
 }
 
 // ---- round r >= 1: keys (rank[i], rank[i+h]) ------------------------------------------------------

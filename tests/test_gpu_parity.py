@@ -168,7 +168,10 @@ FORCED_PATHS = [
     ({"DARK_BWT_SORT_VARIANT": "5"}, "dna", 1, 700001),
     ({"DARK_BWT_TILE_BY_BLOCKIDX": "1"}, "mixed", 9, 900001),
     ({"DARK_BWT_RANK_SEARCH": "0"}, "dna", 6, 1500003),              # selective rank fill (bitmap + SA sweep) instead of the search
-    ({"DARK_BWT_PAIRS": "0"}, "mixed", 4, 1300001),                  # late rounds WITHOUT the pairs kernel
+    ({"DARK_BWT_PAIRS": "0"}, "mixed", 4, 1300001),
+    ({"DARK_BWT_FUSED_INIT": "0"}, "mixed", 4, 900001),              # initial keys materialised instead of built inside pass 1
+    ({"DARK_BWT_FUSED_INIT": "0"}, "dna", 2, 1100003),
+    ({"DARK_BWT_FORCE_U64_STATUS": "1"}, "dna", 8, 600011),          # key-generating pass with 64-bit tile status                  # late rounds WITHOUT the pairs kernel
     ({"DARK_BWT_INLINE_EMIT": "0"}, "dna", 3, 1200007),              # pruned initial sort WITHOUT inline emission
     ({"DARK_BWT_INLINE_EMIT": "0", "DARK_BWT_EMIT_WINDOW_MB": "1"}, "dna", 4, 3000001),        # tiles ordered by blockIdx instead of the claim counter
 ]
@@ -516,3 +519,36 @@ def test_pairs_mode_rounds(saca, oracle, torch, name):
         assert st["pair_rounds"] > 0 and st2["pair_rounds"] > 0, (st["pair_rounds"], st2["pair_rounds"])
     prof = oracle.profile(t, sa_o)
     assert st2["active"][1:1 + len(prof["m"])] == prof["m"], (st2["active"], prof["m"])
+
+
+def test_qgram_histogram_equals_per_key_histogram(oracle):
+    """DARK_BWT_CHECK_HIST=1 makes the library count the round-0 digit histograms both ways (one q-gram
+    histogram of the text vs eight digits per key) and fail on any difference; alphabets of 2, 4, 16 and 256
+    symbols, sizes around the 56-position boundary correction, an unaligned device pointer."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, oracle\n"
+        "from dark_b200 import saca, _ffi\n"
+        "rng = np.random.default_rng(5)\n"
+        "for sigma in (2, 3, 4, 11, 16, 200, 256):\n"
+        "    for n in (2, 3, 5, 8, 17, 55, 56, 57, 63, 64, 65, 100, 4097, 300007):\n"
+        "        t = rng.integers(0, sigma, n).astype(np.uint8)\n"
+        "        if sigma < 200: t = t * 7 + 3\n"
+        "        with saca.Constructor(n) as c:\n"
+        "            b, o, s = c.bwt_and_sa(t)\n"
+        "        bo, oo, so = oracle.bwt_forward(t, want_sa=True)\n"
+        "        assert o == oo and np.array_equal(b, bo) and np.array_equal(s, so), (sigma, n)\n"
+        "n = 100003\n"
+        "t = rng.integers(0, 4, n + 1).astype(np.uint8)\n"
+        "d = torch.from_numpy(t).cuda()\n"
+        "db = torch.empty(n, dtype=torch.uint8, device='cuda')\n"
+        "with saca.Constructor(n, flags=_ffi.F_DEVICE_ONLY) as c:\n"
+        "    o = c.bwt_device(d.data_ptr() + 1, n, db.data_ptr(), None)\n"
+        "bo, oo = oracle.bwt_forward(np.ascontiguousarray(t[1:]))\n"
+        "assert o == oo and np.array_equal(db.cpu().numpy(), bo)\n"
+        "print('ok')\n")
+    env = dict(os.environ, DARK_BWT_CHECK_HIST="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
