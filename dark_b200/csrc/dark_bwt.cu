@@ -118,6 +118,7 @@ struct dark_bwt_ctx {
     };
     std::vector<Span> spans;
     int next_counter = 0;
+    u32 tag = 0;  // bit carried by isa[] entries of active suffixes during forward_device (0: not used)
     u32 launches = 0;
     char err[320] = {0};
 
@@ -317,10 +318,12 @@ int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32
     if (int rc = next_counter(ctx, &counter)) return rc;
     CK(cudaMemsetAsync(ctx->scan_words, 0, sizeof(u64) * kScanWordsPerTile * tiles, ctx->stream));
     ScanTileState ts{ctx->scan_words};
+    static const char* pfe = getenv("DARK_BWT_RERANK_PREFETCH");
+    const u32 prefetch_ahead = pfe ? (u32)atoi(pfe) : 0u;
     k_rerank<kScanThreads, kScanItems, ROUND0, PAIRS><<<tiles, kScanThreads, 0, ctx->stream>>>(
         keys, ids, ROUND0 ? nullptr : ctx->ranks, m, n, K, kb, ctx->isa, sa, out_ids, ROUND0 ? ctx->ranks : ctx->ranks_alt, ts, counter,
         &ctx->mail_dev->count, sink.ids, sink.vals,
-        ctx->bucket_hist, sink.shift, text, bwt_inline, &ctx->mail_dev->origin);
+        ctx->bucket_hist, sink.shift, text, bwt_inline, &ctx->mail_dev->origin, prefetch_ahead, ROUND0 ? 0u : ctx->tag);
     LAUNCHED();
     if (!ROUND0) std::swap(ctx->ranks, ctx->ranks_alt);
     return 0;
@@ -329,14 +332,14 @@ int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32
 // Bucketed scatter, step 2 and 3: histogram (already in ctx->bucket_hist) -> cursors, partition the
 // `count` pairs into (out_ids, out_vals), then write isa[] bucket by bucket.
 int bucket_partition(dark_bwt_ctx* ctx, const u32* pair_ids, const u32* pair_vals, u32 count, int shift, u32* out_ids,
-                     u32* out_vals) {
+                     u32* out_vals, u32 or_mask = 0) {
     const u32 blocks = (u32)ceil_div(count, 256 * 16);
     if (pair_vals)
         k_partition_pairs<256, 16, false><<<blocks, 256, 0, ctx->stream>>>(pair_ids, pair_vals, count, shift, ctx->bucket_hist,
-                                                                           out_ids, out_vals);
+                                                                           out_ids, out_vals, or_mask);
     else
         k_partition_pairs<256, 16, true><<<blocks, 256, 0, ctx->stream>>>(pair_ids, nullptr, count, shift, ctx->bucket_hist,
-                                                                          out_ids, out_vals);
+                                                                          out_ids, out_vals, 0u);
     LAUNCHED();
     return 0;
 }
@@ -572,6 +575,12 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     // survive; otherwise only the survivors' now, and per round the few that are actually read.
     bool isa_complete = true;
     int selective_rounds = 0;
+    // isa[] entries of active suffixes carry bit 31 (blocks up to 2^31 bytes): the text-order key builder finds
+    // them by it.  DARK_BWT_TEXT_BUILD=0 switches tag and builder off; =<k> uses the builder while m > n/k.
+    const char* tev = getenv("DARK_BWT_TEXT_BUILD");
+    const int text_div = tev ? atoi(tev) : 8;
+    const u32 tag = (text_div > 0 && (u64)n <= (1ull << 31)) ? 0x80000000u : 0u;
+    ctx->tag = tag;
     const char* pev = getenv("DARK_BWT_PAIRS");
     const bool use_pairs = pev ? atoi(pev) != 0 : true;
     bool pairs_mode = false;
@@ -592,14 +601,14 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
                 u32* oi = (u32*)ctx->keys[0];
                 u32* ov = (u32*)ctx->keys[1];
                 if (int rc = bucket_partition(ctx, sa, nullptr, n, bshift, oi, ov)) return rc;
-                if (int rc = bucket_partition(ctx, ctx->ids[cur], ctx->ranks, m, bshift, oi, ov)) return rc;
+                if (int rc = bucket_partition(ctx, ctx->ids[cur], ctx->ranks, m, bshift, oi, ov, tag)) return rc;
                 if (int rc = bucket_scatter(ctx, oi, ov, n)) return rc;
             } else {
-                k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, m, ctx->isa);
+                k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, m, ctx->isa, tag);
                 LAUNCHED();
             }
         } else {
-            k_scatter_ranks<256><<<(u32)ceil_div(m, 256), 256, 0, ctx->stream>>>(ctx->ids[cur], ctx->ranks, m, ctx->isa);
+            k_scatter_ranks<256><<<(u32)ceil_div(m, 256), 256, 0, ctx->stream>>>(ctx->ids[cur], ctx->ranks, m, ctx->isa, tag);
             LAUNCHED();
             isa_complete = false;
         }
@@ -627,7 +636,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
             CK(cudaStreamSynchronize(ctx->stream));
             if (ctx->mail->flag == 0) {
                 if (!isa_complete) {
-                    k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, 0u, ctx->isa);
+                    k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, 0u, ctx->isa, tag);
                     LAUNCHED();
                     isa_complete = true;
                 }
@@ -646,7 +655,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
             ScanTileState ts{ctx->scan_words};
             k_pairs_round<kPairThreads, kPairsPerThread><<<tiles, kPairThreads, 0, ctx->stream>>>(
                 ctx->ids[cur], ctx->ranks, m, n, h, ctx->isa, reinterpret_cast<uint2*>(ctx->keys[0]), sa, ctx->ids[cur ^ 1], ctx->ranks_alt, ts, counter,
-                &ctx->mail_dev->count, d_text, bwt_inline, &ctx->mail_dev->origin);
+                &ctx->mail_dev->count, d_text, bwt_inline, &ctx->mail_dev->origin, tag);
             LAUNCHED();
             std::swap(ctx->ranks, ctx->ranks_alt);
             span_end(ctx, sp);
@@ -693,15 +702,34 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
                 LAUNCHED();
                 ++selective_rounds;
             } else {  // still not done after two rounds: fill every settled rank once
-                k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, 0u, ctx->isa);
+                k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, 0u, ctx->isa, tag);
                 LAUNCHED();
                 isa_complete = true;
             }
         }
+        bool text_built = false;
+        if (!keys_built && tag != 0 && isa_complete && (u64)m * (u64)text_div > (u64)n) {
+            // many suffixes still active: sweep isa[] in text order instead of gathering from it (k_build_keys_text)
+            constexpr int kTextThreads = 512, kTextItems = 8;
+            const u32 tiles = (u32)ceil_div(n, kTextThreads * kTextItems);
+            if (tiles > ctx->scan_tiles) return ctx->fail_internal("scan tile state too small");
+            u32* counter = nullptr;
+            if (int rc = next_counter(ctx, &counter)) return rc;
+            CK(cudaMemsetAsync(ctx->scan_words, 0, sizeof(u64) * kScanWordsPerTile * tiles, ctx->stream));
+            auto kern = k_build_keys_text<kTextThreads, kTextItems>;
+            const size_t smem = kBuildTextSmem<kTextThreads, kTextItems>;
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const u32 grid = std::min<u32>(tiles, (u32)ctx->num_sms * 3);
+            kern<<<grid, kTextThreads, smem, ctx->stream>>>(ctx->isa, n, h, kb, tag, ctx->keys[cur], ctx->ids[cur], ctx->scan_words, counter,
+                                                            &ctx->mail_dev->flag, ctx->hist, passes_r);
+            LAUNCHED();
+            keys_built = true;
+            text_built = true;
+        }
         if (!keys_built) {
             const u32 blocks = (u32)ceil_div(m, kBuildThreads * kBuildItems);  // one tile per CTA: the gathers want every warp slot filled
             k_build_keys<kBuildThreads, kBuildItems><<<blocks, kBuildThreads, 0, ctx->stream>>>(
-                ctx->ids[cur], ctx->ranks, m, n, h, kb, ctx->isa, ctx->keys[cur], ctx->hist, passes_r);
+                ctx->ids[cur], ctx->ranks, m, n, h, kb, ctx->isa, tag, ctx->keys[cur], ctx->hist, passes_r);
             LAUNCHED();
         }
         span_end(ctx, sp);
@@ -729,7 +757,9 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         }
         span_end(ctx, sp);
         cur ^= 1;
+        const u32 m_sorted = m;
         if (int rc = fetch_count(ctx, &m)) return rc;
+        if (text_built && ctx->mail->flag != m_sorted) return ctx->fail_internal("tagged isa[] entries disagree with the active list");
         h *= 2;
         ++round;
     }

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kRadix) k_gram_expand(const u8* __restrict__ t
 template <int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS)
 k_build_keys(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m, u32 n, u64 h, int kb,
-             const u32* __restrict__ isa, u64* __restrict__ keys_out, u32* __restrict__ g_hist, int num_passes) {
+             const u32* __restrict__ isa, u32 tag, u64* __restrict__ keys_out, u32* __restrict__ g_hist, int num_passes) {
     __shared__ u32 s_hist[kMaxPasses * kRadix];
     const int tid = threadIdx.x;
     hist_clear(s_hist, tid, THREADS);
@@ -276,7 +276,7 @@ k_build_keys(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m, 
         for (int k = 0; k < ITEMS; ++k) {
             const u64 p = base + k * THREADS + tid;
             const u64 pos2 = (u64)id[k] + h;
-            r2[k] = (p < m && pos2 < n) ? __ldg(isa + pos2) + 1u : 0u;
+            r2[k] = (p < m && pos2 < n) ? (__ldg(isa + pos2) & ~tag) + 1u : 0u;
         }
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
@@ -286,6 +286,141 @@ k_build_keys(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m, 
                 keys_out[p] = key;
                 hist_add_key(s_hist, key, 0, num_passes);
             }
+        }
+    }
+    __syncthreads();
+    hist_flush(s_hist, g_hist, num_passes, tid, THREADS);
+}
+
+// The same keys built in TEXT order.  isa[] entries of active suffixes carry `tag` (bit 31, blocks of at most
+// 2^31 bytes), so a sweep over isa[] finds them; rank2 = isa[i+h] is then a second sequential stream instead
+// of a random gather (110 B of DRAM traffic per gathered rank once isa[] outgrows L2,
+// profiles/r1_ncu_c5_c3_v2.md).  The active list comes out in text order instead of rank order, which the sort
+// does not care about: it orders by (rank, rank2) from scratch, and the re-rank reads the exact ranks
+// position-wise from the old list, whose group layout the sorted list reproduces.
+// HBM: 4n read (+ the second stream, mostly L2 hits), 12 m written.  Used while m > n/8.
+template <int THREADS, int ITEMS>
+constexpr size_t kBuildTextSmem = (size_t)THREADS * ITEMS * 12 + (size_t)kMaxPasses * kRadix * 4;
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+k_build_keys_text(const u32* __restrict__ isa, u32 n, u64 h, int kb, u32 tag, u64* __restrict__ keys_out, u32* __restrict__ ids_out,
+                  u64* __restrict__ scan_words, u32* __restrict__ tile_counter, u32* __restrict__ out_count,
+                  u32* __restrict__ g_hist, int num_passes) {
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int WARPS = THREADS / 32;
+    static_assert(ITEMS % 4 == 0, "128-bit loads");
+    extern __shared__ __align__(16) unsigned char smem_text_build[];  // kBuildTextSmem<THREADS, ITEMS> bytes
+    u64* s_key = reinterpret_cast<u64*>(smem_text_build);
+    u32* s_id = reinterpret_cast<u32*>(s_key + TILE);
+    u32* s_hist = s_id + TILE;
+    __shared__ u32 s_warp[WARPS];
+    __shared__ u32 s_excl, s_total, s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    hist_clear(s_hist, tid, THREADS);
+    const u32 ntiles = (u32)(((u64)n + TILE - 1) / TILE);
+    for (;;) {  // persistent CTAs: one histogram flush per CTA, tiles numbered in claim order for the look-back
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= ntiles) break;
+        const u64 i0 = (u64)tile * TILE + (u64)tid * ITEMS;  // blocked: a thread owns ITEMS consecutive suffixes
+        u32 r1[ITEMS], r2[ITEMS];
+        if (i0 + ITEMS <= n) {
+            const uint4* v = reinterpret_cast<const uint4*>(isa + i0);
+#pragma unroll
+            for (int k = 0; k < ITEMS / 4; ++k) {
+                const uint4 q = v[k];
+                r1[4 * k] = q.x;
+                r1[4 * k + 1] = q.y;
+                r1[4 * k + 2] = q.z;
+                r1[4 * k + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) r1[k] = i0 + k < n ? isa[i0 + k] : 0u;
+        }
+        u32 act = 0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k)
+            if (r1[k] & tag) act |= 1u << k;
+        const u64 j0 = i0 + h;
+        if (act) {
+            if ((h & 3) == 0 && j0 + ITEMS <= n) {
+                const uint4* v = reinterpret_cast<const uint4*>(isa + j0);
+#pragma unroll
+                for (int k = 0; k < ITEMS / 4; ++k) {
+                    const uint4 q = v[k];
+                    r2[4 * k] = (q.x & ~tag) + 1u;
+                    r2[4 * k + 1] = (q.y & ~tag) + 1u;
+                    r2[4 * k + 2] = (q.z & ~tag) + 1u;
+                    r2[4 * k + 3] = (q.w & ~tag) + 1u;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k) r2[k] = (((act >> k) & 1u) && j0 + k < n) ? (__ldg(isa + j0 + k) & ~tag) + 1u : 0u;
+            }
+        }
+        // exclusive scan of the active counts: thread -> warp -> tile -> look-back on one self-flagged word
+        const u32 mine = __popc(act);
+        u32 incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        u32 wprefix = 0;
+        for (int w = 0; w < warp; ++w) wprefix += s_warp[w];
+        if (warp == 0) {
+            u32 total = 0;
+            for (int w = 0; w < WARPS; ++w) total += s_warp[w];
+            u64* word = scan_words + (size_t)tile * 4 + 2;
+            u32 excl = 0;
+            if (tile == 0) {
+                if (lane == 0) st_relaxed(word, ((u64)2 << 62) | total);
+            } else {
+                if (lane == 0) st_relaxed(word, ((u64)1 << 62) | total);
+                int base = (int)tile - 1;
+                for (;;) {
+                    const int t = base - lane;
+                    u64 w2 = (u64)2 << 62;
+                    if (t >= 0) {
+                        const u64* theirs = scan_words + (size_t)t * 4 + 2;
+                        do { w2 = ld_relaxed(theirs); } while ((w2 >> 62) == 0);
+                    }
+                    const u32 im = __ballot_sync(0xffffffffu, (w2 >> 62) == 2);
+                    const int first = im ? (__ffs(im) - 1) : 31;
+                    excl += __reduce_add_sync(0xffffffffu, lane <= first ? (u32)w2 : 0u);
+                    if (im) break;
+                    base -= 32;
+                }
+                if (lane == 0) st_relaxed(word, ((u64)2 << 62) | (excl + total));
+            }
+            if (lane == 0) {
+                s_excl = excl;
+                s_total = total;
+                if (tile + 1 == ntiles) *out_count = excl + total;
+            }
+        }
+        // stage the tile's keys compacted in shared memory, then write them out lane-consecutively
+        u32 lq = wprefix + incl - mine;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            if ((act >> k) & 1u) {
+                const u64 key = ((u64)((r1[k] & ~tag) >> 1) << kb) | r2[k];
+                s_key[lq] = key;
+                s_id[lq] = (u32)(i0 + k);
+                hist_add_key(s_hist, key, 0, num_passes);
+                ++lq;
+            }
+        }
+        __syncthreads();
+        const u32 total = s_total, excl = s_excl;
+        for (u32 i = tid; i < total; i += THREADS) {
+            keys_out[excl + i] = s_key[i];
+            ids_out[excl + i] = s_id[i];
         }
     }
     __syncthreads();
@@ -391,9 +526,10 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
          u32* __restrict__ isa, u32* __restrict__ sa, u32* __restrict__ out_ids, u32* __restrict__ out_ranks, ScanTileState ts,
          u32* __restrict__ tile_counter, u32* __restrict__ out_count, u32* __restrict__ pair_ids,
          u32* __restrict__ pair_vals, u32* __restrict__ pair_hist, int pair_shift, const u8* __restrict__ text,
-         u8* __restrict__ bwt_inline, u64* __restrict__ origin) {
+         u8* __restrict__ bwt_inline, u64* __restrict__ origin, u32 prefetch_ahead, u32 tag) {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
+    static_assert(TILE / 8 <= THREADS, "one prefetch per thread covers the tile");
     __shared__ ScanTriple s_warp[WARPS];
     __shared__ ScanTriple s_excl;
     __shared__ u32 s_tile;
@@ -409,6 +545,18 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     __syncthreads();
     const u32 tile = s_tile;
     const u64 p0 = (u64)tile * TILE + (u64)tid * ITEMS;  // blocked arrangement
+    if (prefetch_ahead) {
+        // pull the input of the tile that will be claimed ~one wave from now into L2: a tile's lifetime is
+        // load latency + look-back, and only two CTAs fit on an SM
+        const u64 q0 = ((u64)tile + prefetch_ahead) * TILE;
+        if (q0 + TILE <= m) {
+            const void* a = nullptr;
+            if (tid < TILE / 16) a = keys + q0 + (u64)tid * 16;  // 128 B lines
+            else if (tid < TILE / 16 + TILE / 32) a = ids + q0 + (u64)(tid - TILE / 16) * 32;
+            else if (!ROUND0 && tid < TILE / 16 + TILE / 16) a = ranks_in + q0 + (u64)(tid - TILE / 16 - TILE / 32) * 32;
+            if (a) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+    }
 
     // keys[p0-1 .. p0+ITEMS], ids[p0 .. p0+ITEMS) (+ neighbours in round 0)
     u64 key[ITEMS + 2];
@@ -632,15 +780,18 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
             // Round 0 leaves isa[] alone: if nothing survives (DNA-like blocks) the ranks are never
             // read, otherwise they are scattered afterwards.  It writes every SA slot
             // (SUF_INVALID for unsettled ones) so that the later fill can tell which slots are final.
+            // isa[] entries of suffixes that stay active carry `tag` (k_build_keys_text finds them by it); a
+            // suffix that settles with its rank unchanged is therefore rewritten too, to drop the tag
+            const bool changed = r_new != r_old || (tag != 0 && single);
+            const u32 r_tagged = r_new | (single ? 0u : tag);
             if (PAIRS) {
-                const bool changed = r_new != r_old;
                 if (changed) {
                     v_pid[k] = sid;
                     atomicAdd(&s_bhist[sid >> pair_shift], 1u);
                 }
-                v_pval[k] = r_new;
-            } else if (!ROUND0 && r_new != r_old) {
-                isa[sid] = r_new;
+                v_pval[k] = r_tagged;
+            } else if (!ROUND0 && changed) {
+                isa[sid] = r_tagged;
             }
             if (ROUND0 && single) v_sa[k] = sid;
             if (bwt_inline != nullptr && single) {
@@ -721,21 +872,21 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_round0_isa(const u32* __restrict__ sa, u32 n, const u32* __restrict__ act_ids, const u32* __restrict__ act_ranks, u32 m,
-             u32* __restrict__ isa) {
+             u32* __restrict__ isa, u32 tag) {
     const u64 p = (u64)blockIdx.x * THREADS + threadIdx.x;
     if (p < n) {
         const u32 v = ld_stream(sa + p);
         if (v != 0xFFFFFFFFu) isa[v] = (u32)p;
     }
-    if (p < m) isa[ld_stream(act_ids + p)] = ld_stream(act_ranks + p);
+    if (p < m) isa[ld_stream(act_ids + p)] = ld_stream(act_ranks + p) | tag;
 }
 
 // Rank scatter of the survivors alone: isa[id] = rank of its group (m elements).
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_scatter_ranks(const u32* __restrict__ act_ids, const u32* __restrict__ act_ranks, u32 m, u32* __restrict__ isa) {
+k_scatter_ranks(const u32* __restrict__ act_ids, const u32* __restrict__ act_ranks, u32 m, u32* __restrict__ isa, u32 tag) {
     const u64 p = (u64)blockIdx.x * THREADS + threadIdx.x;
-    if (p < m) isa[ld_stream(act_ids + p)] = ld_stream(act_ranks + p);
+    if (p < m) isa[ld_stream(act_ids + p)] = ld_stream(act_ranks + p) | tag;
 }
 
 // Four pairs per thread (128-bit loads): the stores are random inside the bucket's L2-resident slice, so
@@ -824,7 +975,7 @@ __global__ void __launch_bounds__(256) k_bucket_scan(u32* __restrict__ g_hist, u
 template <int THREADS, int ITEMS, bool VAL_IS_INDEX>
 __global__ void __launch_bounds__(THREADS)
 k_partition_pairs(const u32* __restrict__ ids, const u32* __restrict__ vals, u32 count, int shift, u32* __restrict__ cursor,
-                  u32* __restrict__ out_ids, u32* __restrict__ out_vals) {
+                  u32* __restrict__ out_ids, u32* __restrict__ out_vals, u32 or_mask) {
     constexpr int TILE = THREADS * ITEMS;
     __shared__ u32 s_ids[TILE];
     __shared__ u32 s_vals[TILE];
@@ -846,7 +997,7 @@ k_partition_pairs(const u32* __restrict__ ids, const u32* __restrict__ vals, u32
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const u64 i = base + k * THREADS + tid;
-        val[k] = VAL_IS_INDEX ? (u32)i : (i < count ? ld_stream(vals + i) : 0u);
+        val[k] = VAL_IS_INDEX ? (u32)i : (i < count ? ld_stream(vals + i) | or_mask : 0u);
     }
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) pos[k] = id[k] != 0xFFFFFFFFu ? atomicAdd(&s_cnt[id[k] >> shift], 1u) : 0u;
@@ -1156,7 +1307,7 @@ __global__ void __launch_bounds__(THREADS)
 k_pairs_round(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m, u32 n, u64 h, const u32* __restrict__ isa_ro,
               uint2* __restrict__ pending, u32* __restrict__ sa, u32* __restrict__ out_ids, u32* __restrict__ out_ranks,
               ScanTileState ts, u32* __restrict__ tile_counter, u32* __restrict__ out_count, const u8* __restrict__ text,
-              u8* __restrict__ bwt_inline, u64* __restrict__ origin) {
+              u8* __restrict__ bwt_inline, u64* __restrict__ origin, u32 tag) {
     constexpr int TILE_PAIRS = THREADS * PPT;
     constexpr int WARPS = THREADS / 32;
     __shared__ u32 s_warp[WARPS];
@@ -1184,8 +1335,8 @@ k_pairs_round(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m,
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
         const u64 pa = (u64)a[k] + h, pb = (u64)b[k] + h;
-        ra[k] = (q0 + k < npairs && pa < n) ? __ldg(isa_ro + pa) + 1u : 0u;
-        rb[k] = (q0 + k < npairs && pb < n) ? __ldg(isa_ro + pb) + 1u : 0u;
+        ra[k] = (q0 + k < npairs && pa < n) ? (__ldg(isa_ro + pa) & ~tag) + 1u : 0u;
+        rb[k] = (q0 + k < npairs && pb < n) ? (__ldg(isa_ro + pb) & ~tag) + 1u : 0u;
     }
     u32 tied = 0;
 #pragma unroll

@@ -169,6 +169,14 @@ FORCED_PATHS = [
     ({"DARK_BWT_TILE_BY_BLOCKIDX": "1"}, "mixed", 9, 900001),
     ({"DARK_BWT_RANK_SEARCH": "0"}, "dna", 6, 1500003),              # selective rank fill (bitmap + SA sweep) instead of the search
     ({"DARK_BWT_PAIRS": "0"}, "mixed", 4, 1300001),
+    ({"DARK_BWT_TEXT_BUILD": "0"}, "mixed", 4, 1100001),             # rank gathers only, isa[] untagged
+    ({"DARK_BWT_TEXT_BUILD": "0"}, "rep17", 2, 700001),
+    ({"DARK_BWT_TEXT_BUILD": "1000000"}, "mixed", 5, 1200001),       # text-order key build in every round that may use it
+    ({"DARK_BWT_TEXT_BUILD": "1000000"}, "rep17", 3, 900001),
+    ({"DARK_BWT_TEXT_BUILD": "1000000"}, "text", 6, 800001),
+    ({"DARK_BWT_TEXT_BUILD": "1000000", "DARK_BWT_BUCKETED": "1"}, "mixed", 6, 2100001),
+    ({"DARK_BWT_TEXT_BUILD": "1000000", "DARK_BWT_BUCKETED": "1"}, "rep17", 4, 1000001),
+    ({"DARK_BWT_TEXT_BUILD": "1000000", "DARK_BWT_RANK_SEARCH": "0"}, "dna", 6, 1500003),
     ({"DARK_BWT_FUSED_INIT": "0"}, "mixed", 4, 900001),              # initial keys materialised instead of built inside pass 1
     ({"DARK_BWT_FUSED_INIT": "0"}, "dna", 2, 1100003),
     ({"DARK_BWT_FORCE_U64_STATUS": "1"}, "dna", 8, 600011),          # key-generating pass with 64-bit tile status                  # late rounds WITHOUT the pairs kernel
