@@ -740,18 +740,20 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
 
         sp = span_begin(ctx, PH_RERANK);
         if (bucketed && m > n / 16) {
-            const size_t ma = align_up((size_t)m, 64);
+            // the re-rank appends each tile's rank updates to per-bucket regions (suffix_kernels.cuh, PAIRS); the
+            // regions are then scattered bucket by bucket, each bucket's slice of isa[] staying in L2
             PairSink sink;
             sink.ids = (u32*)ctx->keys[cur ^ 1];
-            sink.vals = sink.ids + ma;
+            sink.vals = sink.ids + align_up((size_t)n, 64);
             sink.shift = bshift;
             CK(cudaMemsetAsync(ctx->bucket_hist, 0, sizeof(u32) * 256, ctx->stream));
             if (int rc = launch_rerank<false, true>(ctx, ctx->keys[cur], ctx->ids[cur], m, n, K, kb, sa, ctx->ids[cur ^ 1], d_text, bwt_inline, sink)) return rc;
-            if (int rc = bucket_scan(ctx)) return rc;
-            u32* oi = (u32*)ctx->keys[cur];  // the sorted keys are dead once the re-rank has run
-            u32* ov = oi + ma;
-            if (int rc = bucket_partition(ctx, sink.ids, sink.vals, m, bshift, oi, ov)) return rc;
-            if (int rc = bucket_scatter(ctx, oi, ov, m)) return rc;
+            u32* chunk_prefix = ctx->bucket_hist + 256;
+            k_region_chunks<<<1, 256, 0, ctx->stream>>>(ctx->bucket_hist, chunk_prefix);
+            LAUNCHED();
+            k_scatter_regions<<<(u32)ceil_div(m, kRegionChunk) + 256, 256, 0, ctx->stream>>>(sink.ids, sink.vals, ctx->bucket_hist, chunk_prefix,
+                                                                                          bshift, ctx->isa);
+            LAUNCHED();
         } else {
             if (int rc = launch_rerank<false, false>(ctx, ctx->keys[cur], ctx->ids[cur], m, n, K, kb, sa, ctx->ids[cur ^ 1], d_text, bwt_inline)) return rc;
         }
@@ -907,7 +909,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     const size_t o_scalars = carve(sizeof(DeviceScalars));
     const size_t o_status = carve(ctx->sort_status_bytes);
     const size_t o_counters = carve(sizeof(u32) * kMaxCounters);
-    const size_t o_bhist = carve(sizeof(u32) * 256);
+    const size_t o_bhist = carve(sizeof(u32) * 1024);  // 256 bucket counters/cursors + 257 chunk prefixes
     const size_t o_bitmap = carve(sizeof(u32) * (ceil_div(N, 32) + 1));
     const size_t o_swords = carve(sizeof(u64) * kScanWordsPerTile * ctx->scan_tiles);
     ctx->arena_bytes = off;

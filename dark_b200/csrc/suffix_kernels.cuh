@@ -517,9 +517,10 @@ constexpr int kScanWordsPerTile = 4;
 constexpr int kLookbackWarps = 4;  // 128 predecessor tiles polled per look-back step
 __device__ __forceinline__ u64 scan_pack(u32 flag, u32 value) { return ((u64)flag << 62) | value; }
 
-// PAIRS (large rounds >= 1): changed ranks are not scattered into isa[] here; element p writes the pair
-// (id, new rank) — (SUF_INVALID, _) if unchanged — to pair_ids[p]/pair_vals[p] and the CTA adds its
-// bucket histogram (id >> pair_shift) to pair_hist for the bucketed scatter that follows.
+// PAIRS (large rounds >= 1): changed ranks are not scattered into isa[] here.  The tile partitions its
+// (id, new rank) updates by bucket = id >> pair_shift in shared memory and appends each bucket's run to that
+// bucket's region of pair_ids/pair_vals (region b starts at element b << pair_shift and can hold every id
+// of the bucket; pair_hist[b] is its fill cursor).  The bucketed scatter that follows reads the regions.
 template <int THREADS, int ITEMS, bool ROUND0, bool PAIRS>
 __global__ void __launch_bounds__(THREADS, 2)
 k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* __restrict__ ranks_in, u32 m, u32 n, int K, int kb,
@@ -536,7 +537,8 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     __shared__ u64 s_lb[2][kLookbackWarps][3];
     __shared__ u32 s_oid[TILE], s_ork[TILE];  // this tile's survivors, staged for coalesced stores
     __shared__ u32 s_tile_cnt;
-    __shared__ u32 s_bhist[PAIRS ? 256 : 1];
+    __shared__ u32 s_bhist[PAIRS ? 256 : 1], s_bcur[PAIRS ? 256 : 1], s_goff[PAIRS ? 256 : 1];
+    __shared__ u32 s_bwarp[8], s_btotal;
     static_assert(WARPS >= kLookbackWarps, "look-back warps");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
@@ -836,23 +838,6 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
                 if (p0 + k < m) bwt_inline[p0 + k] = (u8)((k < 4 ? v_b0 >> (8 * k) : v_b1 >> (8 * (k - 4))) & 0xFFu);
         }
     }
-    if (PAIRS) {
-        if (p0 + ITEMS <= m) {
-            uint4* o = reinterpret_cast<uint4*>(pair_ids + p0);
-            o[0] = make_uint4(v_pid[0], v_pid[1], v_pid[2], v_pid[3]);
-            o[1] = make_uint4(v_pid[4], v_pid[5], v_pid[6], v_pid[7]);
-            uint4* q = reinterpret_cast<uint4*>(pair_vals + p0);
-            q[0] = make_uint4(v_pval[0], v_pval[1], v_pval[2], v_pval[3]);
-            q[1] = make_uint4(v_pval[4], v_pval[5], v_pval[6], v_pval[7]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < ITEMS; ++k)
-                if (p0 + k < m) {
-                    pair_ids[p0 + k] = v_pid[k];
-                    pair_vals[p0 + k] = v_pval[k];
-                }
-        }
-    }
     __syncthreads();
     {
         const u32 tile_cnt = s_tile_cnt;
@@ -862,8 +847,42 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
         }
     }
     if (PAIRS) {
-        for (int i = tid; i < 256; i += THREADS)
-            if (s_bhist[i]) atomicAdd(&pair_hist[i], s_bhist[i]);
+        static_assert(!PAIRS || THREADS >= 256, "one thread per bucket");
+        // bucket starts inside the tile; one global atomicAdd per (tile, bucket) reserves the run
+        const u32 c = tid < 256 ? s_bhist[tid] : 0u;
+        u32 incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (tid < 256 && lane == 31) s_bwarp[warp] = incl;
+        __syncthreads();  // also: the survivors have left s_oid/s_ork
+        if (tid < 256) {
+            u32 wbase = 0;
+            for (int w = 0; w < warp; ++w) wbase += s_bwarp[w];
+            const u32 start = wbase + incl - c;
+            s_bcur[tid] = start;
+            s_goff[tid] = ((u32)tid << pair_shift) + (c ? atomicAdd(&pair_hist[tid], c) : 0u) - start;
+            if (tid == 255) s_btotal = start + c;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            if (v_pid[k] != 0xFFFFFFFFu) {
+                const u32 q = atomicAdd(&s_bcur[v_pid[k] >> pair_shift], 1u);
+                s_oid[q] = v_pid[k];
+                s_ork[q] = v_pval[k];
+            }
+        }
+        __syncthreads();
+        const u32 total = s_btotal;
+        for (u32 i = tid; i < total; i += THREADS) {
+            const u32 v = s_oid[i];
+            const u32 o = s_goff[v >> pair_shift] + i;
+            pair_ids[o] = v;
+            pair_vals[o] = s_ork[i];
+        }
     }
 }
 
@@ -907,6 +926,63 @@ k_scatter_ranks_counted(const u32* __restrict__ ids, const u32* __restrict__ val
         isa[i4.w] = v4.w;
     } else {
         for (u64 q = p; q < total; ++q) isa[ids[q]] = vals[q];
+    }
+}
+
+// Scatter of bucket regions filled by the PAIRS re-rank: region b holds counts[b] pairs from element
+// b << shift on.  chunk_prefix[b] = number of kRegionChunk-sized chunks in the regions before b (k_region_chunks);
+// block x finds its (bucket, chunk) in it.  The grid is the host-side bound ceil(m / chunk) + 256.
+constexpr u32 kRegionChunk = 4096;
+__global__ void __launch_bounds__(256) k_region_chunks(const u32* __restrict__ counts, u32* __restrict__ chunk_prefix) {
+    __shared__ u32 s_warp[8];
+    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    const u32 c = (counts[d] + kRegionChunk - 1) / kRegionChunk;
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    u32 base = 0;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    chunk_prefix[d] = base + incl - c;
+    if (d == 255) chunk_prefix[256] = base + incl;
+}
+__global__ void __launch_bounds__(256)
+k_scatter_regions(const u32* __restrict__ ids, const u32* __restrict__ vals, const u32* __restrict__ counts,
+                  const u32* __restrict__ chunk_prefix, int shift, u32* __restrict__ isa) {
+    __shared__ u32 s_prefix[257];
+    const int tid = threadIdx.x;
+    s_prefix[tid] = chunk_prefix[tid];
+    if (tid == 0) s_prefix[256] = chunk_prefix[256];
+    __syncthreads();
+    const u32 x = blockIdx.x;
+    if (x >= s_prefix[256]) return;
+    int lo = 0, hi = 255;  // last bucket whose prefix is <= x (empty buckets share a prefix with their successor)
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_prefix[mid] <= x) lo = mid;
+        else hi = mid - 1;
+    }
+    const u32 b = (u32)lo;
+    const u32 first = (x - s_prefix[b]) * kRegionChunk, count = counts[b];
+    const u64 base = ((u64)b << shift) + first;
+    const u32 len = min(kRegionChunk, count - first);
+    const bool vec = (base & 3) == 0;  // regions of tiny blocks (shift < 2) may start unaligned
+    for (u32 q = tid * 4; q < len; q += 256 * 4) {
+        if (vec && q + 4 <= len) {
+            uint4 i4, v4;
+            asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(i4.x), "=r"(i4.y), "=r"(i4.z), "=r"(i4.w) : "l"(ids + base + q));
+            asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w) : "l"(vals + base + q));
+            isa[i4.x] = v4.x;
+            isa[i4.y] = v4.y;
+            isa[i4.z] = v4.z;
+            isa[i4.w] = v4.w;
+        } else {
+            for (u32 e = q; e < min(q + 4, len); ++e) isa[ids[base + e]] = vals[base + e];
+        }
     }
 }
 
