@@ -57,7 +57,6 @@ struct DeviceScalars {  // mirrors Mailbox on the device
     float collide[kMaxPasses];
     u64 origin;
     unsigned long long bad;
-    u32 pair_total;  // device only: number of valid pairs of the current bucketed scatter
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -329,8 +328,8 @@ int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32
     return 0;
 }
 
-// Bucketed scatter, step 2 and 3: histogram (already in ctx->bucket_hist) -> cursors, partition the
-// `count` pairs into (out_ids, out_vals), then write isa[] bucket by bucket.
+// Bucketed scatter of round 0: partition the `count` pairs by id >> shift into per-bucket regions of
+// (out_ids, out_vals) — region b starts at element b << shift, ctx->bucket_hist[b] is its fill cursor.
 int bucket_partition(dark_bwt_ctx* ctx, const u32* pair_ids, const u32* pair_vals, u32 count, int shift, u32* out_ids,
                      u32* out_vals, u32 or_mask = 0) {
     const u32 blocks = (u32)ceil_div(count, 256 * 16);
@@ -343,20 +342,12 @@ int bucket_partition(dark_bwt_ctx* ctx, const u32* pair_ids, const u32* pair_val
     LAUNCHED();
     return 0;
 }
-int bucket_hist_add(dark_bwt_ctx* ctx, const u32* ids, u32 count, int shift) {
-    const u32 blocks = (u32)std::min<u64>(ceil_div(count, 256 * 8), 148 * 8);
-    k_bucket_hist<256><<<std::max(blocks, 1u), 256, 0, ctx->stream>>>(ids, count, shift, ctx->bucket_hist);
+// Scatter of the per-bucket regions (counts in ctx->bucket_hist) into isa[], bucket by bucket.
+int region_scatter(dark_bwt_ctx* ctx, const u32* ids, const u32* vals, u32 upper, int shift) {
+    u32* chunk_prefix = ctx->bucket_hist + 256;
+    k_region_chunks<<<1, 256, 0, ctx->stream>>>(ctx->bucket_hist, chunk_prefix);
     LAUNCHED();
-    return 0;
-}
-int bucket_scan(dark_bwt_ctx* ctx) {
-    k_bucket_scan<<<1, 256, 0, ctx->stream>>>(ctx->bucket_hist, &ctx->scalars->pair_total);
-    LAUNCHED();
-    return 0;
-}
-int bucket_scatter(dark_bwt_ctx* ctx, const u32* out_ids, const u32* out_vals, u32 upper) {
-    k_scatter_ranks_counted<256><<<(u32)ceil_div(ceil_div(upper, 4), 256), 256, 0, ctx->stream>>>(out_ids, out_vals, &ctx->scalars->pair_total,
-                                                                                      ctx->isa);
+    k_scatter_regions<<<(u32)ceil_div(upper, kRegionChunk) + 256, 256, 0, ctx->stream>>>(ids, vals, ctx->bucket_hist, chunk_prefix, shift, ctx->isa);
     LAUNCHED();
     return 0;
 }
@@ -595,14 +586,11 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         if (m > n / 16) {
             if (bucketed) {  // every suffix gets its rank: settled ones their slot, survivors their group rank
                 CK(cudaMemsetAsync(ctx->bucket_hist, 0, sizeof(u32) * 256, ctx->stream));
-                if (int rc = bucket_hist_add(ctx, sa, n, bshift)) return rc;
-                if (int rc = bucket_hist_add(ctx, ctx->ids[cur], m, bshift)) return rc;
-                if (int rc = bucket_scan(ctx)) return rc;
                 u32* oi = (u32*)ctx->keys[0];
                 u32* ov = (u32*)ctx->keys[1];
                 if (int rc = bucket_partition(ctx, sa, nullptr, n, bshift, oi, ov)) return rc;
                 if (int rc = bucket_partition(ctx, ctx->ids[cur], ctx->ranks, m, bshift, oi, ov, tag)) return rc;
-                if (int rc = bucket_scatter(ctx, oi, ov, n)) return rc;
+                if (int rc = region_scatter(ctx, oi, ov, n, bshift)) return rc;
             } else {
                 k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, m, ctx->isa, tag);
                 LAUNCHED();
@@ -748,12 +736,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
             sink.shift = bshift;
             CK(cudaMemsetAsync(ctx->bucket_hist, 0, sizeof(u32) * 256, ctx->stream));
             if (int rc = launch_rerank<false, true>(ctx, ctx->keys[cur], ctx->ids[cur], m, n, K, kb, sa, ctx->ids[cur ^ 1], d_text, bwt_inline, sink)) return rc;
-            u32* chunk_prefix = ctx->bucket_hist + 256;
-            k_region_chunks<<<1, 256, 0, ctx->stream>>>(ctx->bucket_hist, chunk_prefix);
-            LAUNCHED();
-            k_scatter_regions<<<(u32)ceil_div(m, kRegionChunk) + 256, 256, 0, ctx->stream>>>(sink.ids, sink.vals, ctx->bucket_hist, chunk_prefix,
-                                                                                          bshift, ctx->isa);
-            LAUNCHED();
+            if (int rc = region_scatter(ctx, sink.ids, sink.vals, m, bshift)) return rc;
         } else {
             if (int rc = launch_rerank<false, false>(ctx, ctx->keys[cur], ctx->ids[cur], m, n, K, kb, sa, ctx->ids[cur ^ 1], d_text, bwt_inline)) return rc;
         }

@@ -908,31 +908,10 @@ k_scatter_ranks(const u32* __restrict__ act_ids, const u32* __restrict__ act_ran
     if (p < m) isa[ld_stream(act_ids + p)] = ld_stream(act_ranks + p) | tag;
 }
 
-// Four pairs per thread (128-bit loads): the stores are random inside the bucket's L2-resident slice, so
-// what matters is how many of them each thread keeps in flight.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-k_scatter_ranks_counted(const u32* __restrict__ ids, const u32* __restrict__ vals, const u32* __restrict__ count, u32* __restrict__ isa) {
-    const u32 total = *count;
-    const u64 p = ((u64)blockIdx.x * THREADS + threadIdx.x) * 4;
-    if (p >= total) return;
-    if (p + 4 <= total) {
-        uint4 i4, v4;
-        asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(i4.x), "=r"(i4.y), "=r"(i4.z), "=r"(i4.w) : "l"(ids + p));
-        asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w) : "l"(vals + p));
-        isa[i4.x] = v4.x;
-        isa[i4.y] = v4.y;
-        isa[i4.z] = v4.z;
-        isa[i4.w] = v4.w;
-    } else {
-        for (u64 q = p; q < total; ++q) isa[ids[q]] = vals[q];
-    }
-}
-
 // Scatter of bucket regions filled by the PAIRS re-rank: region b holds counts[b] pairs from element
 // b << shift on.  chunk_prefix[b] = number of kRegionChunk-sized chunks in the regions before b (k_region_chunks);
 // block x finds its (bucket, chunk) in it.  The grid is the host-side bound ceil(m / chunk) + 256.
-constexpr u32 kRegionChunk = 4096;
+constexpr u32 kRegionChunk = 1024;  // one 128-bit load pair and four stores per thread
 __global__ void __launch_bounds__(256) k_region_chunks(const u32* __restrict__ counts, u32* __restrict__ chunk_prefix) {
     __shared__ u32 s_warp[8];
     const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
@@ -1014,39 +993,6 @@ k_fill_needed(const u32* __restrict__ sa, u32 n, const u32* __restrict__ bitmap,
 // of id — unstable, so shared-memory atomics give the in-tile position and one global atomicAdd per
 // (tile, bucket) reserves the output run: no look-back chain; (2) scatter bucket by bucket, where
 // each bucket's slice of isa[] (n/256 ranks) stays in L2 and leaves as full sectors.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-k_bucket_hist(const u32* __restrict__ ids, u32 count, int shift, u32* __restrict__ g_hist) {
-    __shared__ u32 s_hist[256];
-    for (int i = threadIdx.x; i < 256; i += THREADS) s_hist[i] = 0;
-    __syncthreads();
-    const u64 stride = (u64)gridDim.x * THREADS;
-    for (u64 i = (u64)blockIdx.x * THREADS + threadIdx.x; i < count; i += stride) {
-        const u32 id = ld_stream(ids + i);
-        if (id != 0xFFFFFFFFu) atomicAdd(&s_hist[id >> shift], 1u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += THREADS)
-        if (s_hist[i]) atomicAdd(&g_hist[i], s_hist[i]);
-}
-// counts -> exclusive bases in place (becomes the per-bucket output cursor); total -> *total_out
-__global__ void __launch_bounds__(256) k_bucket_scan(u32* __restrict__ g_hist, u32* __restrict__ total_out) {
-    __shared__ u32 s_warp[8];
-    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
-    const u32 c = g_hist[d];
-    u32 incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    u32 base = 0;
-    for (int w = 0; w < warp; ++w) base += s_warp[w];
-    g_hist[d] = base + incl - c;
-    if (d == 255) *total_out = base + incl;
-}
 // VAL_IS_INDEX: the value of element i is i itself (rank of a settled suffix = its SA slot).
 template <int THREADS, int ITEMS, bool VAL_IS_INDEX>
 __global__ void __launch_bounds__(THREADS)
@@ -1091,7 +1037,8 @@ k_partition_pairs(const u32* __restrict__ ids, const u32* __restrict__ vals, u32
     for (int w = 0; w < warp; ++w) wbase += s_warp[w];
     const u32 start = wbase + incl - c;
     s_start[tid] = start;
-    s_goff[tid] = (c ? atomicAdd(&cursor[tid], c) : 0u) - start;
+    // cursor[b] counts from 0; bucket b's region starts at element b << shift (it can hold every id of the bucket)
+    s_goff[tid] = ((u32)tid << shift) + (c ? atomicAdd(&cursor[tid], c) : 0u) - start;
     u32 total = 0;
     for (int w = 0; w < 8; ++w) total += s_warp[w];
     __syncthreads();
