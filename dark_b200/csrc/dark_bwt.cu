@@ -614,8 +614,9 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         }
         // Once every remaining group is a pair the rounds switch to the pairs kernel for good (groups
         // only ever split).  The check reads the rank list once and costs a host round trip, so it is skipped
-        // while most of the block is still active (period-17: ten rounds of giant groups).
-        if (use_pairs && !pairs_mode && (m & 1u) == 0 && (round == 1 || m <= n / 2)) {
+        // while most of the block is still active (period-17: ten rounds of giant groups).  The kernel gathers
+        // from isa[], so it waits until every rank is there (few survivors after round 0: the selective rounds).
+        if (use_pairs && !pairs_mode && isa_complete && (m & 1u) == 0 && (round == 1 || m <= n / 2)) {
             ctx->mail->flag = 0;
             u32* seen = nullptr;
             if (int rc = next_counter(ctx, &seen)) return rc;
@@ -623,11 +624,6 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
             LAUNCHED();
             CK(cudaStreamSynchronize(ctx->stream));
             if (ctx->mail->flag == 0) {
-                if (!isa_complete) {
-                    k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(sa, n, ctx->ids[cur], ctx->ranks, 0u, ctx->isa, tag);
-                    LAUNCHED();
-                    isa_complete = true;
-                }
                 pairs_mode = true;
             }
         }

@@ -699,9 +699,12 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
                 u64 w0 = scan_pack(2u, 0u), w1 = w0, w2 = w0;  // virtual tiles before tile 0: inclusive identity
                 if (t >= 0) {
                     const u64* theirs = ts.words + (size_t)t * kScanWordsPerTile;
-                    do { w0 = ld_relaxed(theirs + 0); } while ((w0 >> 62) == 0);
-                    do { w1 = ld_relaxed(theirs + 1); } while ((w1 >> 62) == 0);
-                    do { w2 = ld_relaxed(theirs + 2); } while ((w2 >> 62) == 0);
+                    // the three loads of a poll are issued together: one L2 round trip per poll, not three
+                    do {
+                        w0 = ld_relaxed(theirs + 0);
+                        w1 = ld_relaxed(theirs + 1);
+                        w2 = ld_relaxed(theirs + 2);
+                    } while (((w0 >> 62) == 0) | ((w1 >> 62) == 0) | ((w2 >> 62) == 0));
                 }
                 // per warp: value up to (and including) its nearest inclusive prefix, and whether it has one
                 u64 part0, part1, part2;
