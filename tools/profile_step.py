@@ -4,6 +4,7 @@
 import json
 import os
 import sys
+import zlib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -26,4 +27,13 @@ for _ in range(reps):
     print(json.dumps({"workload": name, "n": n, "origin": origin, **{k: st[k] for k in (
         "sigma", "symbols_per_key", "initial_symbols", "rounds", "sort_passes", "kernel_launches", "device_ms", "init_ms", "sort_ms", "pass_ms",
         "keybuild_ms", "rerank_ms", "emit_ms", "active", "passes")}}))
+# the timing is only worth reading if the bytes are right: CRC-32 of the BWT against the committed oracle fixture
+gold = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_golden.json")))
+key = "%s:%d:%d" % (kind, seed, n)
+if key in gold and not os.environ.get("DARK_BWT_PASS_KNOCKOUT"):
+    crc = "%08x" % (zlib.crc32(db.cpu().numpy().tobytes()) & 0xFFFFFFFF)
+    ok = crc == gold[key]["bwt_crc32"] and origin == gold[key]["origin"]
+    print(json.dumps({"workload": name, "parity": "ok" if ok else "MISMATCH", "bwt_crc32": crc}))
+    if not ok:
+        sys.exit(3)
 con.close()
