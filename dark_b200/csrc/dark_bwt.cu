@@ -36,6 +36,7 @@ constexpr int kInitItems = 16;
 constexpr int kBuildThreads = 256;
 constexpr int kBuildItems = 8;
 constexpr int kMaxCounters = 1024;
+constexpr u32 kMaxManyBlocks = DARK_BWT_MAX_MANY_BLOCKS;
 constexpr int kMaxEvents = 16 + 10 * DARK_BWT_MAX_ROUNDS;
 
 enum Phase { PH_INIT = 0, PH_SORT, PH_PASS, PH_KEYBUILD, PH_RERANK, PH_EMIT, PH_COUNT };
@@ -102,6 +103,9 @@ struct dark_bwt_ctx {
     u64* scan_words = nullptr;
     long long* pass_trace = nullptr;  // debug: per-tile phase stamps of the radix pass (dark_bwt_debug_trace)
     u32* bucket_hist = nullptr;  // 256 counters / cursors of the bucketed rank scatter
+    u32* many_starts = nullptr;            // dark_bwt_forward_many: block offsets (kMaxManyBlocks + 1)
+    unsigned long long* many_origins = nullptr;  // ... per-block origins
+    u16* many_lut = nullptr;               // ... byte -> code 1..sigma
     u32* bitmap = nullptr;  // n bits: positions whose rank the next round reads
     size_t scan_tiles = 0;
 
@@ -758,6 +762,118 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     return DARK_BWT_OK;
 }
 
+// Many independent blocks in one sort (suffix_kernels.cuh, "many small blocks").  d_text holds the blocks back
+// to back, ctx->many_starts their offsets (B + 1 values, already on the device); d_bwt receives the per-block BWTs
+// at the same offsets, ctx->many_origins the origins.
+int forward_many_device(dark_bwt_ctx* ctx, const u8* d_text, u32 n, u32 B, u8* d_bwt, u32* d_sa_out, dark_bwt_stats* st) {
+    CK(cudaSetDevice(ctx->device));
+    ctx->n_events = 0;
+    ctx->spans.clear();
+    ctx->next_counter = 0;
+    ctx->launches = 0;
+    ctx->tag = 0;
+    if (st) {
+        const float h2d = st->h2d_ms;
+        memset(st, 0, sizeof(*st));
+        st->h2d_ms = h2d;
+        st->n = n;
+        st->active[0] = n;
+    }
+    const int e_first = ctx->n_events++;
+    CK(cudaEventRecord(ctx->events[e_first], ctx->stream));
+    int sp = span_begin(ctx, PH_INIT);
+    CK(cudaMemsetAsync(ctx->counters, 0, sizeof(u32) * kMaxCounters, ctx->stream));
+    CK(cudaMemsetAsync(ctx->present, 0, sizeof(u32) * 256, ctx->stream));
+    CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
+    {
+        const u32 blocks = (u32)std::min<u64>(ceil_div(ceil_div(n, 16), 256), 148 * 8);
+        k_symbol_presence<256><<<std::max(blocks, 1u), 256, 0, ctx->stream>>>(d_text, n, ctx->present);
+        LAUNCHED();
+        k_many_lut<<<1, 256, 0, ctx->stream>>>(ctx->present, ctx->many_lut, &ctx->mail_dev->sigma);
+        LAUNCHED();
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    const u32 sigma = ctx->mail->sigma;
+    if (sigma < 1 || sigma > 256) return ctx->fail_internal("alphabet scan returned an impossible sigma");
+    const int s_bits = bit_length(sigma);  // codes 1..sigma, 0 = past the end of the block
+    const int K = 64 / s_bits;
+    if (st) {
+        st->sigma = sigma;
+        st->bits_per_symbol = s_bits;
+        st->symbols_per_key = K;
+        st->initial_symbols = K;
+    }
+    const u32 grid = (u32)std::min<u64>(ceil_div(n, 256), (u64)ctx->num_sms * 8);
+    k_many_init_keys<256><<<grid, 256, 0, ctx->stream>>>(d_text, n, ctx->many_lut, s_bits, K, ctx->many_starts, B, ctx->keys[0], ctx->ids[0],
+                                                         ctx->hist);
+    LAUNCHED();
+    span_end(ctx, sp);
+
+    int cur = 0;
+    sp = span_begin(ctx, PH_SORT);
+    if (int rc = run_sort(ctx, ctx->keys, ctx->ids, cur, n, 0, kMaxPasses, &cur, st, 0)) return rc;
+    span_end(ctx, sp);
+    sp = span_begin(ctx, PH_RERANK);
+    // no "short suffix" special case (K = 1 disables it): the padding code 0 orders proper prefixes first
+    if (int rc = launch_rerank<true, false>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, 1, 0, ctx->sa, ctx->ids[cur ^ 1], d_text, nullptr)) return rc;
+    span_end(ctx, sp);
+    cur ^= 1;
+    u32 m = 0;
+    if (int rc = fetch_count(ctx, &m)) return rc;
+    if (m > 0) {
+        k_round0_isa<256><<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(ctx->sa, n, ctx->ids[cur], ctx->ranks, m, ctx->isa, 0u);
+        LAUNCHED();
+    }
+    const int kb = bit_length((u64)n + B);  // rank2 in [0, n + B]
+    const int key_bits = kb + bit_length(((u64)n - 1) >> 1);
+    if (key_bits > 64) return ctx->fail_internal("batch too large for 64-bit keys");
+    const int passes_r = (key_bits + kRadixBits - 1) / kRadixBits;
+    u64 h = (u64)K;
+    int round = 1;
+    while (m > 0) {
+        if (round >= DARK_BWT_MAX_ROUNDS || h >= 2 * (u64)n + 2) return ctx->fail_internal("prefix doubling did not converge");
+        if (st) {
+            st->active[round] = m;
+            st->rounds = round;
+        }
+        sp = span_begin(ctx, PH_KEYBUILD);
+        CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
+        const u32 g2 = (u32)std::min<u64>(ceil_div(m, 256), (u64)ctx->num_sms * 8);
+        k_many_build_keys<256><<<g2, 256, 0, ctx->stream>>>(ctx->ids[cur], ctx->ranks, m, h, kb, ctx->isa, ctx->many_starts, B, ctx->keys[cur],
+                                                            ctx->hist, passes_r);
+        LAUNCHED();
+        span_end(ctx, sp);
+        sp = span_begin(ctx, PH_SORT);
+        if (int rc = run_sort(ctx, ctx->keys, ctx->ids, cur, m, 0, passes_r, &cur, st, round)) return rc;
+        span_end(ctx, sp);
+        sp = span_begin(ctx, PH_RERANK);
+        if (int rc = launch_rerank<false, false>(ctx, ctx->keys[cur], ctx->ids[cur], m, n, K, kb, ctx->sa, ctx->ids[cur ^ 1], d_text, nullptr)) return rc;
+        span_end(ctx, sp);
+        cur ^= 1;
+        if (int rc = fetch_count(ctx, &m)) return rc;
+        h *= 2;
+        ++round;
+    }
+    // bring every block's suffixes together (stable sort of the interleaved SA by block number), then emit
+    sp = span_begin(ctx, PH_EMIT);
+    const int bits = std::max(1, bit_length((u64)B - 1));
+    const int passes_b = (bits + kRadixBits - 1) / kRadixBits;
+    CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
+    k_many_blocks_of_sa<256><<<grid, 256, 0, ctx->stream>>>(ctx->sa, n, ctx->many_starts, B, ctx->keys[0], ctx->ids[0], ctx->hist, passes_b);
+    LAUNCHED();
+    cur = 0;
+    if (int rc = run_sort(ctx, ctx->keys, ctx->ids, cur, n, 0, passes_b, &cur, nullptr, 0)) return rc;
+    k_many_emit<<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(ctx->keys[cur], ctx->ids[cur], n, d_text, ctx->many_starts, d_bwt,
+                                                               ctx->many_origins, d_sa_out);
+    LAUNCHED();
+    span_end(ctx, sp);
+    const int e_last = ctx->n_events++;
+    CK(cudaEventRecord(ctx->events[e_last], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    finish_stats(ctx, st, e_first, e_last);
+    return DARK_BWT_OK;
+}
+
 // Inverse BWT on device buffers (kernels and method: suffix_kernels.cuh, "inverse BWT").
 int inverse_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, u64 origin64, u8* d_text, float* ms_out) {
     if (n64 < 1 || n64 > ctx->capacity || n64 > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;
@@ -891,6 +1007,9 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     const size_t o_bhist = carve(sizeof(u32) * 1024);  // 256 bucket counters/cursors + 257 chunk prefixes
     const size_t o_bitmap = carve(sizeof(u32) * (ceil_div(N, 32) + 1));
     const size_t o_swords = carve(sizeof(u64) * kScanWordsPerTile * ctx->scan_tiles);
+    const size_t o_mstarts = carve(sizeof(u32) * (kMaxManyBlocks + 1));
+    const size_t o_morigins = carve(sizeof(unsigned long long) * kMaxManyBlocks);
+    const size_t o_mlut = carve(sizeof(u16) * 256);
     ctx->arena_bytes = off;
 
     auto bail = [&](int code) {
@@ -924,6 +1043,9 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     ctx->scan_words = (u64*)(base + o_swords);
     ctx->bitmap = (u32*)(base + o_bitmap);
     ctx->bucket_hist = (u32*)(base + o_bhist);
+    ctx->many_starts = (u32*)(base + o_mstarts);
+    ctx->many_origins = (unsigned long long*)(base + o_morigins);
+    ctx->many_lut = (u16*)(base + o_mlut);
 
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DARK_BWT_E_CUDA);
     if (staging) {
@@ -1047,6 +1169,69 @@ int dark_bwt_forward_batch(dark_bwt_ctx* ctx, const uint8_t* const* texts, const
     }
     CK(cudaStreamSynchronize(ctx->copy_out));
     CK(cudaStreamSynchronize(ctx->copy_in));
+    return DARK_BWT_OK;
+}
+
+int dark_bwt_forward_many(dark_bwt_ctx* ctx, const uint8_t* const* texts, const uint64_t* ns, uint8_t* const* bwt_outs,
+                          uint64_t* origins_out, uint64_t count, dark_bwt_stats* stats) {
+    if (!ctx || !texts || !ns || !bwt_outs || !origins_out) return DARK_BWT_E_INVALID_ARG;
+    if (ctx->flags & DARK_BWT_F_DEVICE_ONLY) return DARK_BWT_E_INVALID_ARG;
+    ctx->err[0] = 0;
+    if (count == 0) return DARK_BWT_OK;
+    if (count > kMaxManyBlocks) return DARK_BWT_E_INVALID_ARG;
+    std::vector<u32> starts(count + 1);
+    u64 total = 0;
+    for (uint64_t k = 0; k < count; ++k) {
+        if (!texts[k] || !bwt_outs[k]) return DARK_BWT_E_INVALID_ARG;
+        if (ns[k] < 2) return DARK_BWT_E_INVALID_N;
+        starts[k] = (u32)total;
+        total += ns[k];
+        if (total > ctx->capacity || total > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;  // the blocks share one arena
+    }
+    starts[count] = (u32)total;
+    CK(cudaSetDevice(ctx->device));
+    cudaEvent_t a = ctx->events[kMaxEvents - 1], b = ctx->events[kMaxEvents - 2];
+    CK(cudaEventRecord(a, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->many_starts, starts.data(), sizeof(u32) * (count + 1), cudaMemcpyHostToDevice, ctx->stream));
+    for (uint64_t k = 0; k < count; ++k)
+        CK(cudaMemcpyAsync(ctx->d_text + starts[k], texts[k], ns[k], cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // `starts` may go out of scope only after the copy
+    float h2d = 0.f;
+    cudaEventElapsedTime(&h2d, a, b);
+    if (stats) stats->h2d_ms = h2d;
+    if (int rc = forward_many_device(ctx, ctx->d_text, (u32)total, (u32)count, ctx->d_bwt, nullptr, stats)) return rc;
+    CK(cudaEventRecord(a, ctx->stream));
+    for (uint64_t k = 0; k < count; ++k)
+        CK(cudaMemcpyAsync(bwt_outs[k], ctx->d_bwt + starts[k], ns[k], cudaMemcpyDeviceToHost, ctx->stream));
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "origins are copied as they are");
+    CK(cudaMemcpyAsync(origins_out, ctx->many_origins, sizeof(uint64_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (stats) cudaEventElapsedTime(&stats->d2h_ms, a, b);
+    return DARK_BWT_OK;
+}
+
+int dark_bwt_forward_many_device(dark_bwt_ctx* ctx, const uint8_t* d_text, const uint32_t* d_starts, uint64_t count,
+                                 uint8_t* d_bwt_out, uint64_t* d_origins_out, uint32_t* d_sa_out, dark_bwt_stats* stats) {
+    if (!ctx || !d_text || !d_starts || !d_bwt_out || !d_origins_out) return DARK_BWT_E_INVALID_ARG;
+    ctx->err[0] = 0;
+    if (count == 0) return DARK_BWT_OK;
+    if (count > kMaxManyBlocks) return DARK_BWT_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<u32> starts(count + 1);
+    CK(cudaMemcpyAsync(starts.data(), d_starts, sizeof(u32) * (count + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (starts[0] != 0) return DARK_BWT_E_INVALID_ARG;
+    for (uint64_t k = 0; k < count; ++k)
+        if (starts[k + 1] < starts[k] + 2) return DARK_BWT_E_INVALID_N;
+    const u64 total = starts[count];
+    if (total > ctx->capacity || total > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;
+    CK(cudaMemcpyAsync(ctx->many_starts, d_starts, sizeof(u32) * (count + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (stats) stats->h2d_ms = 0.f;
+    if (int rc = forward_many_device(ctx, d_text, (u32)total, (u32)count, d_bwt_out, d_sa_out, stats)) return rc;
+    CK(cudaMemcpyAsync(d_origins_out, ctx->many_origins, sizeof(uint64_t) * count, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return DARK_BWT_OK;
 }
 

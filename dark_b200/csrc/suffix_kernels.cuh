@@ -1439,6 +1439,120 @@ k_pairs_round(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m,
     }
 }
 
+// ---- many small blocks in one sort (dark_bwt_forward_many) ----------------------------------------
+// B independent blocks are concatenated (block b = text[starts[b] .. starts[b+1])) and their suffixes sorted
+// together; a suffix ends at the end of ITS block.  Symbols get dense codes 1..sigma and code 0 pads a key past
+// the block end, so a suffix that is a proper prefix of another sorts first without the single-block
+// descending-id device (App. A.3).  In the doubling rounds "past the end of block b" reads as rank 1+b and real
+// ranks as isa+1+B: equal suffixes of different blocks are ordered by block number, so the sort terminates.
+// The resulting suffix array interleaves the blocks; one stable radix sort by block number brings every block's
+// suffixes together, in their own lexicographic order, at the block's offsets (k_many_blocks_of_sa, k_many_emit).
+// These kernels favour simplicity: a C1-sized block is launch-latency bound on its own (33 launches for 768 KB).
+__device__ __forceinline__ u32 block_of(const u32* __restrict__ starts, u32 B, u32 i) {  // largest b with starts[b] <= i
+    u32 lo = 0, hi = B - 1;
+    while (lo < hi) {
+        const u32 mid = (lo + hi + 1) >> 1;
+        if (__ldg(starts + mid) <= i) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+__global__ void __launch_bounds__(256) k_many_lut(const u32* __restrict__ present, u16* __restrict__ lut16, u32* __restrict__ sigma_out) {
+    __shared__ u32 s_warp[8];
+    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    const u32 c = present[d] ? 1u : 0u;
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    u32 base = 0;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    lut16[d] = (u16)(c ? base + incl : 0u);  // codes 1..sigma
+    if (d == 255) *sigma_out = base + incl;
+}
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_many_init_keys(const u8* __restrict__ text, u32 n, const u16* __restrict__ lut16, int s_bits, int K, const u32* __restrict__ starts,
+                 u32 B, u64* __restrict__ keys_out, u32* __restrict__ ids_out, u32* __restrict__ g_hist) {
+    __shared__ u32 s_hist[kMaxPasses * kRadix];
+    __shared__ u16 s_lut[256];
+    const int tid = threadIdx.x;
+    hist_clear(s_hist, tid, THREADS);
+    for (int i = tid; i < 256; i += THREADS) s_lut[i] = lut16[i];
+    __syncthreads();
+    for (u64 i = (u64)blockIdx.x * THREADS + tid; i < n; i += (u64)gridDim.x * THREADS) {
+        const u32 b = block_of(starts, B, (u32)i);
+        const u64 end = __ldg(starts + b + 1);
+        u64 key = 0;
+        for (int c = 0; c < K; ++c) key = (key << s_bits) | (i + c < end ? (u64)s_lut[text[i + c]] : 0ull);
+        key <<= (64 - s_bits * K);
+        keys_out[i] = key;
+        ids_out[i] = (u32)i;
+        hist_add_key(s_hist, key, 0, kMaxPasses);
+    }
+    __syncthreads();
+    hist_flush(s_hist, g_hist, kMaxPasses, tid, THREADS);
+}
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_many_build_keys(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m, u64 h, int kb, const u32* __restrict__ isa,
+                  const u32* __restrict__ starts, u32 B, u64* __restrict__ keys_out, u32* __restrict__ g_hist, int num_passes) {
+    __shared__ u32 s_hist[kMaxPasses * kRadix];
+    const int tid = threadIdx.x;
+    hist_clear(s_hist, tid, THREADS);
+    __syncthreads();
+    for (u64 p = (u64)blockIdx.x * THREADS + tid; p < m; p += (u64)gridDim.x * THREADS) {
+        const u32 id = ids[p];
+        const u32 b = block_of(starts, B, id);
+        const u64 pos2 = (u64)id + h;
+        const u64 r2 = pos2 < __ldg(starts + b + 1) ? (u64)__ldg(isa + pos2) + 1u + B : 1u + b;
+        const u64 key = ((u64)(ranks[p] >> 1) << kb) | r2;
+        keys_out[p] = key;
+        hist_add_key(s_hist, key, 0, num_passes);
+    }
+    __syncthreads();
+    hist_flush(s_hist, g_hist, num_passes, tid, THREADS);
+}
+// (block number, suffix) pairs of the interleaved suffix array, for the stable sort by block number
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_many_blocks_of_sa(const u32* __restrict__ sa, u32 n, const u32* __restrict__ starts, u32 B, u64* __restrict__ keys_out,
+                    u32* __restrict__ ids_out, u32* __restrict__ g_hist, int num_passes) {
+    __shared__ u32 s_hist[kMaxPasses * kRadix];
+    const int tid = threadIdx.x;
+    hist_clear(s_hist, tid, THREADS);
+    __syncthreads();
+    for (u64 j = (u64)blockIdx.x * THREADS + tid; j < n; j += (u64)gridDim.x * THREADS) {
+        const u32 id = sa[j];
+        const u64 key = block_of(starts, B, id);
+        keys_out[j] = key;
+        ids_out[j] = id;
+        hist_add_key(s_hist, key, 0, num_passes);
+    }
+    __syncthreads();
+    hist_flush(s_hist, g_hist, num_passes, tid, THREADS);
+}
+// position p of the sorted list is slot p - starts[b] of block b: its BWT byte, the block's origin, its SA entry
+__global__ void __launch_bounds__(256)
+k_many_emit(const u64* __restrict__ blk, const u32* __restrict__ ids, u32 n, const u8* __restrict__ text, const u32* __restrict__ starts,
+            u8* __restrict__ bwt, unsigned long long* __restrict__ origins, u32* __restrict__ sa_out) {
+    const u64 p = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (p >= n) return;
+    const u32 b = (u32)blk[p], id = ids[p];
+    const u32 first = __ldg(starts + b);
+    if (id == first) {
+        bwt[p] = text[__ldg(starts + b + 1) - 1];
+        origins[b] = p - first;
+    } else {
+        bwt[p] = text[id - 1];
+    }
+    if (sa_out != nullptr) sa_out[p] = id - first;
+}
+
 // Debug statistic (DARK_BWT_GROUP_STATS=1): largest group of the active list (capped at 4096) and the
 // number of groups, from the rank list (equal rank = same group, groups are contiguous).
 __global__ void __launch_bounds__(256) k_group_stats(const u32* __restrict__ ranks, u32 m, u32* __restrict__ out /* [0]=max size, [1]=groups */) {

@@ -113,6 +113,31 @@ class Constructor:
         origins = self.bwt_batch_into([t.ctypes.data for t in ts], [t.size for t in ts], [o.ctypes.data for o in outs])
         return list(zip(outs, origins))
 
+    def bwt_many_into(self, text_ptrs, ns, bwt_ptrs):
+        """Many small host blocks in ONE device sort (dark_bwt_forward_many): raw host addresses; returns the origins.
+        The blocks share the context's arena: sum(ns) <= capacity."""
+        cnt = len(ns)
+        assert len(text_ptrs) == cnt and len(bwt_ptrs) == cnt
+        T = (ctypes.c_void_p * cnt)(*text_ptrs)
+        B = (ctypes.c_void_p * cnt)(*bwt_ptrs)
+        N = (ctypes.c_uint64 * cnt)(*[int(x) for x in ns])
+        O = (ctypes.c_uint64 * cnt)()
+        _ffi.check(self._L.dark_bwt_forward_many(self._ctx, T, N, B, O, cnt, ctypes.byref(self.stats)), self._ctx,
+                   "Constructor::bwt_many")
+        return [int(O[i]) for i in range(cnt)]
+
+    def bwt_many(self, blocks):
+        """[(bwt, origin), ...] for a list of small host blocks, sorted together in one pass over the GPU."""
+        ts = [_as_u8(b) for b in blocks]
+        outs = [np.empty(t.size, dtype=np.uint8) for t in ts]
+        origins = self.bwt_many_into([t.ctypes.data for t in ts], [t.size for t in ts], [o.ctypes.data for o in outs])
+        return list(zip(outs, origins))
+
+    def bwt_many_device(self, d_text, d_starts, count, d_bwt, d_origins, d_sa=None):
+        """Device-resident form: blocks back to back in d_text, offsets d_starts[0..count] (u32, on the device)."""
+        _ffi.check(self._L.dark_bwt_forward_many_device(self._ctx, d_text, d_starts, int(count), d_bwt, d_origins, d_sa,
+                                                        ctypes.byref(self.stats)), self._ctx, "Constructor::bwt_many_device")
+
     # -- the unpack side: compress::bwt::decode(&input, origin, &mut suffixes)  (block/dc.rs:154-156) ---------
     def inverse(self, bwt, origin):
         """Original block (np.uint8[n]) from its BWT bytes and origin index."""

@@ -114,6 +114,21 @@ int dark_bwt_forward(dark_bwt_ctx *ctx, const uint8_t *text, uint64_t n, uint8_t
 int dark_bwt_forward_batch(dark_bwt_ctx *ctx, const uint8_t *const *texts, const uint64_t *ns, uint8_t *const *bwt_outs,
                            uint64_t *origins_out, uint32_t *const *sa_outs, uint64_t count, dark_bwt_stats *stats);
 
+/* MANY SMALL blocks in ONE sort.  A block the size of the reference's CPU test file (768 KB) keeps a B200 busy
+ * for a fraction of its 0.5 ms of launches; `count` such blocks (each >= 2 bytes, sum <= capacity, count <=
+ * DARK_BWT_MAX_MANY_BLOCKS) are concatenated and their suffixes sorted together, every suffix ending at the end
+ * of its own block.  Results are identical to `count` dark_bwt_forward calls: bwt_outs[k][0..ns[k]) and
+ * origins_out[k].  One H2D copy per block into one device text, one device pass, one D2H copy per block.
+ * (src/main.rs:87-113: the reference's CLI feeds its blocks one after another through one Encoder.) */
+#define DARK_BWT_MAX_MANY_BLOCKS 65536u
+int dark_bwt_forward_many(dark_bwt_ctx *ctx, const uint8_t *const *texts, const uint64_t *ns, uint8_t *const *bwt_outs,
+                          uint64_t *origins_out, uint64_t count, dark_bwt_stats *stats);
+/* Same on device buffers: d_text holds the blocks back to back, d_starts[0..count] their offsets (d_starts[0] = 0,
+ * d_starts[count] = total bytes); d_bwt_out gets the BWTs at the same offsets, d_origins_out[0..count) the origins,
+ * d_sa_out (nullable) the per-block suffix arrays (block-relative indices) at the same offsets. */
+int dark_bwt_forward_many_device(dark_bwt_ctx *ctx, const uint8_t *d_text, const uint32_t *d_starts, uint64_t count,
+                                 uint8_t *d_bwt_out, uint64_t *d_origins_out, uint32_t *d_sa_out, dark_bwt_stats *stats);
+
 /* Same on DEVICE buffers (d_text, d_bwt_out, d_sa_out live on the context's device;
  * d_sa_out nullable; origin_out and stats are host pointers).  No readable slack after
  * d_text[n-1] is required.  Returns after the work has completed on the stream. */

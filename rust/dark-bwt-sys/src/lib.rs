@@ -43,6 +43,11 @@ extern "C" {
                             origin_out: *mut u64, sa_out: *mut u32, stats: *mut dark_bwt_stats) -> c_int;
     pub fn dark_bwt_forward_batch(ctx: *mut dark_bwt_ctx, texts: *const *const u8, ns: *const u64, bwt_outs: *const *mut u8,
                                   origins_out: *mut u64, sa_outs: *const *mut u32, count: u64, stats: *mut dark_bwt_stats) -> c_int;
+    pub fn dark_bwt_forward_many(ctx: *mut dark_bwt_ctx, texts: *const *const u8, ns: *const u64, bwt_outs: *const *mut u8,
+                                 origins_out: *mut u64, count: u64, stats: *mut dark_bwt_stats) -> c_int;
+    pub fn dark_bwt_forward_many_device(ctx: *mut dark_bwt_ctx, d_text: *const u8, d_starts: *const u32, count: u64,
+                                        d_bwt_out: *mut u8, d_origins_out: *mut u64, d_sa_out: *mut u32,
+                                        stats: *mut dark_bwt_stats) -> c_int;
     pub fn dark_bwt_forward_device(ctx: *mut dark_bwt_ctx, d_text: *const u8, n: u64, d_bwt_out: *mut u8,
                                    origin_out: *mut u64, d_sa_out: *mut u32, stats: *mut dark_bwt_stats) -> c_int;
     pub fn dark_bwt_inverse(ctx: *mut dark_bwt_ctx, bwt: *const u8, n: u64, origin: u64, text_out: *mut u8) -> c_int;

@@ -70,6 +70,20 @@ impl Constructor {
         (out, origin as usize)
     }
 
+    /// Many small blocks in one pass over the GPU (`dark_bwt_forward_many`): `(bwt, origin)` per block, each
+    /// identical to `self.bwt(block)`.  The blocks share the arena: their lengths must sum to <= capacity.
+    pub fn bwt_many(&mut self, blocks: &[&[Symbol]]) -> Vec<(Vec<Symbol>, usize)> {
+        let mut outs: Vec<Vec<u8>> = blocks.iter().map(|b| vec![0u8; b.len()]).collect();
+        let texts: Vec<*const u8> = blocks.iter().map(|b| b.as_ptr()).collect();
+        let ns: Vec<u64> = blocks.iter().map(|b| b.len() as u64).collect();
+        let bwts: Vec<*mut u8> = outs.iter_mut().map(|o| o.as_mut_ptr()).collect();
+        let mut origins = vec![0u64; blocks.len()];
+        let rc = unsafe { sys::dark_bwt_forward_many(self.ctx, texts.as_ptr(), ns.as_ptr(), bwts.as_ptr(),
+            origins.as_mut_ptr(), blocks.len() as u64, ptr::null_mut()) };
+        check(self.ctx, rc, "saca::Constructor::bwt_many");
+        outs.into_iter().zip(origins.into_iter().map(|o| o as usize)).collect()
+    }
+
     /// Temporarily provide the storage for outside needs
     pub fn reuse<'a>(&'a mut self) -> &'a mut [Suffix] {
         let (mut p, mut cnt) = (ptr::null_mut(), 0u64);

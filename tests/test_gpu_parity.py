@@ -560,3 +560,71 @@ def test_qgram_histogram_equals_per_key_histogram(oracle):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+# ---- many small blocks in one sort (dark_bwt_forward_many) ---------------------------------------
+def _many_cases():
+    rng = np.random.default_rng(11)
+    from dark_b200 import synth
+    text = synth.generate("text", 3, 200_000)
+    cases = {
+        "two_tiny": [b"abracadabra", b"banana"],
+        "identical_blocks": [b"mississippi"] * 5 + [b"banana"] * 3,      # equal suffixes in different blocks: ordered by block
+        "prefix_blocks": [b"aaaa", b"aaaaaaaa", b"aa", b"aaab", b"baaa"],
+        "minimal": [b"ab", b"ba", b"aa", b"\x00\x00", b"\xff\x00"],
+        "binary_256": [rng.integers(0, 256, int(s)).astype(np.uint8).tobytes() for s in (300, 70_001, 2, 4096, 65_537)],
+        "dna_ragged": [(rng.integers(0, 4, int(s)).astype(np.uint8) + 65).tobytes() for s in rng.integers(2, 50_000, 40)],
+        "text_slices": [text[i:i + 9973].tobytes() for i in range(0, 190_000, 9973)],
+        "periodic": [bytes(range(1, 18)) * 500, bytes(range(1, 18)) * 400 + b"x", b"\x07" * 30_000, b"\x07" * 29_999],
+        "one_block": [text[:50_001].tobytes()],
+    }
+    return cases
+
+
+@pytest.mark.parametrize("name", ["two_tiny", "identical_blocks", "prefix_blocks", "minimal", "binary_256", "dna_ragged",
+                                  "text_slices", "periodic", "one_block"])
+def test_many_small_blocks_in_one_sort(saca, oracle, torch, name):
+    """dark_bwt_forward_many must give, block by block, exactly what the oracle gives for the block alone."""
+    blocks = _many_cases()[name]
+    total = sum(len(b) for b in blocks)
+    with saca.Constructor(max(total, 2)) as con:
+        res = con.bwt_many(blocks)
+        assert len(res) == len(blocks)
+        for k, (blk, (bwt, origin)) in enumerate(zip(blocks, res)):
+            bwt_o, origin_o = oracle.bwt_forward(blk)
+            assert origin == origin_o, (name, k, origin, origin_o)
+            assert np.array_equal(bwt, bwt_o), (name, k)
+        # the same context still does single blocks afterwards
+        b1, o1 = con.bwt(blocks[0])
+        bo, oo = oracle.bwt_forward(blocks[0])
+        assert o1 == oo and np.array_equal(b1, bo)
+
+
+def test_many_blocks_device_form_with_suffix_arrays(saca, oracle, torch):
+    rng = np.random.default_rng(12)
+    blocks = [rng.integers(0, 3, int(s)).astype(np.uint8) for s in (1000, 2, 33_333, 7, 12_345)]
+    starts = np.concatenate([[0], np.cumsum([b.size for b in blocks])]).astype(np.uint32)
+    n = int(starts[-1])
+    from dark_b200 import _ffi
+    with saca.Constructor(n, flags=_ffi.F_DEVICE_ONLY) as con:
+        dt = torch.from_numpy(np.concatenate(blocks)).cuda()
+        ds = torch.from_numpy(starts.view(np.int32)).cuda()
+        db = torch.empty(n, dtype=torch.uint8, device="cuda")
+        do = torch.empty(len(blocks), dtype=torch.int64, device="cuda")
+        dsa = torch.empty(n, dtype=torch.int32, device="cuda")
+        con.bwt_many_device(dt.data_ptr(), ds.data_ptr(), len(blocks), db.data_ptr(), do.data_ptr(), dsa.data_ptr())
+        hb, ho, hs = db.cpu().numpy(), do.cpu().numpy(), dsa.cpu().numpy().view(np.uint32)
+    for k, blk in enumerate(blocks):
+        bwt_o, origin_o, sa_o = oracle.bwt_forward(blk, want_sa=True)
+        a, e = int(starts[k]), int(starts[k + 1])
+        assert int(ho[k]) == origin_o and np.array_equal(hb[a:e], bwt_o) and np.array_equal(hs[a:e], sa_o)
+
+
+def test_many_blocks_rejects_bad_arguments(saca, torch):
+    from dark_b200 import _ffi
+    with saca.Constructor(1000) as con:
+        with pytest.raises(_ffi.DarkBwtError):
+            con.bwt_many([b"ab", b"x"])            # a block of one byte (the reference panics for n = 1, saca.rs:69)
+        with pytest.raises(_ffi.DarkBwtError):
+            con.bwt_many([b"a" * 600, b"b" * 600])  # the blocks share one arena: 1200 > capacity
+        assert con.bwt_many([]) == []
