@@ -28,7 +28,10 @@ using namespace dark;
 namespace {
 
 constexpr int kSortTile = 3072;  // smallest tile of any pass variant (sizes the status buffer)
-constexpr int kScanThreads = 512;
+#ifndef DARK_SCAN_THREADS
+#define DARK_SCAN_THREADS 512
+#endif
+constexpr int kScanThreads = DARK_SCAN_THREADS;  // tuning builds: -DDARK_SCAN_THREADS=256 (profiles/r1_ncu_rerank_final.md)
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 constexpr int kInitThreads = 256;

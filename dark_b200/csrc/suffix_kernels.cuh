@@ -514,7 +514,10 @@ struct ScanTileState {
     u64* words;  // [tiles][4]  (gs1, hs1, cnt, pad)
 };
 constexpr int kScanWordsPerTile = 4;
-constexpr int kLookbackWarps = 4;  // 128 predecessor tiles polled per look-back step
+#ifndef DARK_LB_WARPS
+#define DARK_LB_WARPS 4
+#endif
+constexpr int kLookbackWarps = DARK_LB_WARPS;  // 32 x this many predecessor tiles polled per look-back step
 __device__ __forceinline__ u64 scan_pack(u32 flag, u32 value) { return ((u64)flag << 62) | value; }
 
 // PAIRS (large rounds >= 1): changed ranks are not scattered into isa[] here.  The tile partitions its
@@ -522,7 +525,7 @@ __device__ __forceinline__ u64 scan_pack(u32 flag, u32 value) { return ((u64)fla
 // bucket's region of pair_ids/pair_vals (region b starts at element b << pair_shift and can hold every id
 // of the bucket; pair_hist[b] is its fill cursor).  The bucketed scatter that follows reads the regions.
 template <int THREADS, int ITEMS, bool ROUND0, bool PAIRS>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* __restrict__ ranks_in, u32 m, u32 n, int K, int kb,
          u32* __restrict__ isa, u32* __restrict__ sa, u32* __restrict__ out_ids, u32* __restrict__ out_ranks, ScanTileState ts,
          u32* __restrict__ tile_counter, u32* __restrict__ out_count, u32* __restrict__ pair_ids,
