@@ -105,6 +105,7 @@ struct dark_bwt_ctx {
     u32* counters = nullptr;
     u64* scan_words = nullptr;
     long long* pass_trace = nullptr;  // debug: per-tile phase stamps of the radix pass (dark_bwt_debug_trace)
+    long long* rerank_trace = nullptr;  // debug: per-tile phase stamps of the round-0 re-rank (dark_bwt_debug_trace_rerank)
     u32* bucket_hist = nullptr;  // 256 counters / cursors of the bucketed rank scatter
     u32* many_starts = nullptr;            // dark_bwt_forward_many: block offsets (kMaxManyBlocks + 1)
     unsigned long long* many_origins = nullptr;  // ... per-block origins
@@ -326,10 +327,14 @@ int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32
     ScanTileState ts{ctx->scan_words};
     static const char* pfe = getenv("DARK_BWT_RERANK_PREFETCH");
     const u32 prefetch_ahead = pfe ? (u32)atoi(pfe) : 0u;
-    k_rerank<kScanThreads, kScanItems, ROUND0, PAIRS><<<tiles, kScanThreads, 0, ctx->stream>>>(
+    auto kern = k_rerank<kScanThreads, kScanItems, ROUND0, PAIRS>;
+    constexpr size_t smem = (size_t)kScanTile * 8;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<tiles, kScanThreads, smem, ctx->stream>>>(
         keys, ids, ROUND0 ? nullptr : ctx->ranks, m, n, K, kb, ctx->isa, sa, out_ids, ROUND0 ? ctx->ranks : ctx->ranks_alt, ts, counter,
         &ctx->mail_dev->count, sink.ids, sink.vals,
-        ctx->bucket_hist, sink.shift, text, bwt_inline, &ctx->mail_dev->origin, prefetch_ahead, ROUND0 ? 0u : ctx->tag);
+        ctx->bucket_hist, sink.shift, text, bwt_inline, &ctx->mail_dev->origin, prefetch_ahead, ROUND0 ? 0u : ctx->tag,
+        ROUND0 ? ctx->rerank_trace : nullptr);
     LAUNCHED();
     if (!ROUND0) std::swap(ctx->ranks, ctx->ranks_alt);
     return 0;
@@ -987,7 +992,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     const size_t N = (size_t)max_n;
     const size_t sort_tiles = ceil_div(N, kSortTile);
     ctx->sort_status_bytes = sort_tiles * kRadix * sizeof(u64);
-    ctx->scan_tiles = ceil_div(N, kScanTile);
+    ctx->scan_tiles = ceil_div(N, std::min(kScanTile, 4096));  // the pairs kernel and the text-order builder scan 4,096-suffix tiles
     const bool staging = !(flags & DARK_BWT_F_DEVICE_ONLY);
 
     size_t off = 0;
@@ -1328,6 +1333,12 @@ int dark_bwt_verify_sa_device(dark_bwt_ctx* ctx, const uint8_t* d_text, uint64_t
 
 // Debug hook (not in the public header): per-tile clock64() stamps of subsequent radix passes are
 // written to d_trace ([tiles][8] long long); nullptr switches tracing off.
+int dark_bwt_debug_trace_rerank(dark_bwt_ctx* ctx, long long* d_trace) {
+    if (!ctx) return DARK_BWT_E_INVALID_ARG;
+    ctx->rerank_trace = d_trace;
+    return DARK_BWT_OK;
+}
+
 int dark_bwt_debug_trace(dark_bwt_ctx* ctx, long long* d_trace) {
     if (!ctx) return DARK_BWT_E_INVALID_ARG;
     ctx->pass_trace = d_trace;

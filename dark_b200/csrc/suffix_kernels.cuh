@@ -530,15 +530,21 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
          u32* __restrict__ isa, u32* __restrict__ sa, u32* __restrict__ out_ids, u32* __restrict__ out_ranks, ScanTileState ts,
          u32* __restrict__ tile_counter, u32* __restrict__ out_count, u32* __restrict__ pair_ids,
          u32* __restrict__ pair_vals, u32* __restrict__ pair_hist, int pair_shift, const u8* __restrict__ text,
-         u8* __restrict__ bwt_inline, u64* __restrict__ origin, u32 prefetch_ahead, u32 tag) {
+         u8* __restrict__ bwt_inline, u64* __restrict__ origin, u32 prefetch_ahead, u32 tag, long long* __restrict__ trace) {
+    // trace != nullptr (tools/rerank_trace.py only): thread 0 stamps clock64() at the phase boundaries of its tile
+#define DARK_RSTAMP(i) do { if (trace && threadIdx.x == 0) trace[(size_t)s_tile * 8 + (i)] = clock64(); } while (0)
+    const long long t_entry = trace ? clock64() : 0;
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
     static_assert(TILE / 8 <= THREADS, "one prefetch per thread covers the tile");
+    static_assert(THREADS / 32 <= 32, "warp aggregates are combined by one loop per thread");
     __shared__ ScanTriple s_warp[WARPS];
     __shared__ ScanTriple s_excl;
     __shared__ u32 s_tile;
     __shared__ u64 s_lb[2][kLookbackWarps][3];
-    __shared__ u32 s_oid[TILE], s_ork[TILE];  // this tile's survivors, staged for coalesced stores
+    extern __shared__ __align__(16) u32 smem_rerank[];  // 8 * TILE bytes (dynamic: 1,024-thread tuning builds exceed 48 KB)
+    u32* s_oid = smem_rerank;         // this tile's survivors, staged for coalesced stores
+    u32* s_ork = smem_rerank + TILE;
     __shared__ u32 s_tile_cnt;
     __shared__ u32 s_bhist[PAIRS ? 256 : 1], s_bcur[PAIRS ? 256 : 1], s_goff[PAIRS ? 256 : 1];
     __shared__ u32 s_bwarp[8], s_btotal;
@@ -549,6 +555,8 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
         for (int i = tid; i < 256; i += THREADS) s_bhist[i] = 0;
     __syncthreads();
     const u32 tile = s_tile;
+    if (trace && tid == 0) trace[(size_t)tile * 8 + 0] = t_entry;
+    DARK_RSTAMP(1);
     const u64 p0 = (u64)tile * TILE + (u64)tid * ITEMS;  // blocked arrangement
     if (prefetch_ahead) {
         // pull the input of the tile that will be claimed ~one wave from now into L2: a tile's lifetime is
@@ -653,6 +661,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
         oldh |= tail;
     }
 
+    DARK_RSTAMP(2);
     // thread aggregate, from the flag words: latest old/new head among the valid elements, survivors
     ScanTriple agg = {0u, 0u, 0u};
     {
@@ -683,6 +692,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     // L2 round trip: the "inclusive prefix known" frontier advances one window per polling step.  A
     // 32-tile window of 2,048-element tiles ran at 1.5-1.9 TB/s (profiles/r1_ncu_c5_c3_v2.md), hence
     // kLookbackWarps warps poll kLookbackWarps*32 predecessors per step and the tiles are 4,096 wide.
+    DARK_RSTAMP(3);
     if (warp < kLookbackWarps) {
         ScanTriple tile_agg = {0u, 0u, 0u};
         for (int w = 0; w < WARPS; ++w) tile_agg = scan_combine(tile_agg, s_warp[w]);
@@ -759,8 +769,10 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
             s_tile_cnt = tile_agg.cnt;
             if ((u64)(tile + 1) * TILE >= m) *out_count = excl.cnt + tile_agg.cnt;  // last tile: survivors in total
         }
+        DARK_RSTAMP(4);
     }
     __syncthreads();
+    DARK_RSTAMP(5);
     ScanTriple run = scan_combine(s_excl, texcl);
 
     // apply.  Stores are shaped for L2: a thread's 8 consecutive words leave as two 128-bit stores,
@@ -844,6 +856,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
                 if (p0 + k < m) bwt_inline[p0 + k] = (u8)((k < 4 ? v_b0 >> (8 * k) : v_b1 >> (8 * (k - 4))) & 0xFFu);
         }
     }
+    DARK_RSTAMP(6);
     __syncthreads();
     {
         const u32 tile_cnt = s_tile_cnt;
@@ -852,6 +865,8 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
             out_ranks[tile_cnt0 + i] = s_ork[i];
         }
     }
+    DARK_RSTAMP(7);
+#undef DARK_RSTAMP
     if (PAIRS) {
         static_assert(!PAIRS || THREADS >= 256, "one thread per bucket");
         // bucket starts inside the tile; one global atomicAdd per (tile, bucket) reserves the run
