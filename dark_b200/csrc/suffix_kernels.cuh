@@ -524,8 +524,11 @@ __device__ __forceinline__ u64 scan_pack(u32 flag, u32 value) { return ((u64)fla
 // (id, new rank) updates by bucket = id >> pair_shift in shared memory and appends each bucket's run to that
 // bucket's region of pair_ids/pair_vals (region b starts at element b << pair_shift and can hold every id
 // of the bucket; pair_hist[b] is its fill cursor).  The bucketed scatter that follows reads the regions.
+#ifndef DARK_RERANK_CTAS
+#define DARK_RERANK_CTAS (1024 / THREADS)
+#endif
 template <int THREADS, int ITEMS, bool ROUND0, bool PAIRS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+__global__ void __launch_bounds__(THREADS, DARK_RERANK_CTAS)
 k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* __restrict__ ranks_in, u32 m, u32 n, int K, int kb,
          u32* __restrict__ isa, u32* __restrict__ sa, u32* __restrict__ out_ids, u32* __restrict__ out_ranks, ScanTileState ts,
          u32* __restrict__ tile_counter, u32* __restrict__ out_count, u32* __restrict__ pair_ids,
