@@ -1236,11 +1236,41 @@ k_ibwt_walk(const u32* __restrict__ psi1 /* psi[r] for r >= 1 at psi1[r-1] */, u
     u64 pos = 0;
     if (WRITE) pos = (u64)(n + 1) - dist[s];  // text position of this splitter's row
     u32 cnt = 0;
+    // WRITE: a sublist spells consecutive text positions; the bytes are gathered into aligned 32-bit words and
+    // stored once per word (the walks are bound by the number of memory transactions, ~55 G/s: one random psi
+    // read per step; a byte store per step made the writing walk 9.3 ms against 5.2 ms for the counting one)
+    const bool word_stores = WRITE && (((uintptr_t)text_out) & 3) == 0;
+    u32 acc = 0, have = 0;
+    u64 wbase = 0;  // text offset of the word being gathered
     do {
-        if (WRITE && r != 0 && pos + cnt < n) text_out[pos + cnt] = (u8)ibwt_first_symbol(s_base, r);
+        if (WRITE && r != 0 && pos + cnt < n) {
+            const u64 q = pos + cnt;
+            const u32 sym = ibwt_first_symbol(s_base, r);
+            if (word_stores) {
+                acc |= sym << (8 * (u32)(q & 3));
+                have |= 1u << (u32)(q & 3);
+                wbase = q & ~3ull;
+                if ((q & 3) == 3) {
+                    if (have == 0xFu) {
+                        *reinterpret_cast<u32*>(text_out + (q & ~3ull)) = acc;
+                    } else {
+                        for (u32 e = 0; e < 4; ++e)
+                            if ((have >> e) & 1u) text_out[(q & ~3ull) + e] = (u8)(acc >> (8 * e));
+                    }
+                    acc = 0;
+                    have = 0;
+                }
+            } else {
+                text_out[q] = (u8)sym;
+            }
+        }
         ++cnt;
         r = r == 0 ? head : __ldg(psi1 + (r - 1));
     } while (!(r % stride == 0 || r == head) && cnt <= n);  // cnt bound: corrupt input must not hang
+    if (WRITE && have) {  // the last, partial word of the sublist
+        for (u32 e = 0; e < 4; ++e)
+            if ((have >> e) & 1u) text_out[wbase + e] = (u8)(acc >> (8 * e));
+    }
     if (!WRITE) {
         len[s] = cnt;
         // the sublist of row 0 ('$', the last node) ends the list: psi[0] wraps to the head
