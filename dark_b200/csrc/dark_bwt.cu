@@ -544,6 +544,8 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     gen.lut = ctx->lut;
     gen.n = n;
     gen.lg_s = lg_s;
+    gen.mode = 0;
+    gen.origin = 0;
     bool gen_used = false;
     if (int rc = run_sort(ctx, ctx->keys, ctx->ids, cur, n, 0, passes0, &cur, st, 0, /*prune=*/!no_pack, &first_pass,
                           want_inline ? d_text : nullptr, &emit_inline, fuse_init ? &gen : nullptr, &gen_used))
@@ -895,16 +897,33 @@ int inverse_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, u64 origin64, u8
     CK(cudaEventRecord(ea, ctx->stream));
     CK(cudaMemsetAsync(ctx->counters, 0, sizeof(u32) * kMaxCounters, ctx->stream));
     CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
-    // step 1: (last-column symbol, row) pairs; stable partition by symbol -> psi
-    k_ibwt_elements<<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(d_bwt, n, origin, ctx->keys[0], ctx->ids[0]);
-    LAUNCHED();
-    {
-        const u32 blocks = (u32)std::min<u64>(ceil_div(n, 256 * 8), (u64)ctx->num_sms * 8);
-        k_digit_hist<256><<<std::max(blocks, 1u), 256, 0, ctx->stream>>>(ctx->keys[0], n, 0, 1, ctx->hist);
-        LAUNCHED();
-    }
+    // step 1: (last-column symbol, row) pairs; stable partition by symbol -> psi.  The pairs are built inside the
+    // radix pass (GEN mode 1) and their digit histogram is the byte histogram of the BWT.
     int cur = 0;
-    if (int rc = run_sort(ctx, ctx->keys, ctx->ids, 0, n, 0, 1, &cur, nullptr, 0)) return rc;
+    {
+        k_build_lut<<<1, 256, 0, ctx->stream>>>(ctx->present, ctx->lut, &ctx->mail_dev->sigma, 1);  // identity codes
+        LAUNCHED();
+        u32* gram = ctx->bucket_hist;
+        CK(cudaMemsetAsync(gram, 0, sizeof(u32) * kRadix, ctx->stream));
+        const u32 blocks = (u32)std::min<u64>(ceil_div(n, 256 * 16), (u64)ctx->num_sms * 8);
+        k_gram_hist<256, 8><<<std::max(blocks, 1u), 256, 0, ctx->stream>>>(d_bwt, n, ctx->lut, gram);
+        LAUNCHED();
+        CK(cudaMemcpyAsync(ctx->hist, gram, sizeof(u32) * kRadix, cudaMemcpyDeviceToDevice, ctx->stream));
+        KeyGen gen;
+        gen.text = d_bwt;
+        gen.lut = ctx->lut;
+        gen.n = n;
+        gen.lg_s = 3;
+        gen.mode = 1;
+        gen.origin = origin;
+        bool gen_used = false;
+        if (int rc = run_sort(ctx, ctx->keys, ctx->ids, 0, n, 0, 1, &cur, nullptr, 0, false, nullptr, nullptr, nullptr, &gen, &gen_used)) return rc;
+        if (!gen_used) {  // one-symbol BWT: the pass is the identity and did not run; psi is the row list itself
+            k_ibwt_elements<<<(u32)ceil_div(n, 256), 256, 0, ctx->stream>>>(d_bwt, n, origin, ctx->keys[0], ctx->ids[0]);
+            LAUNCHED();
+            cur = 0;
+        }
+    }
     const u32* psi1 = ctx->ids[cur];
     // step 2: sublists between splitters
     const char* se = getenv("DARK_BWT_IBWT_STRIDE");  // rows between splitters (sweeps only)

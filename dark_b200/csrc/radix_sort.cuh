@@ -225,6 +225,8 @@ struct KeyGen {
     const u8* lut;  // byte -> dense code
     u32 n;
     int lg_s;       // log2(bits per symbol): s in {1, 2, 4, 8}
+    int mode;       // 0: suffix keys of round 0;  1: inverse BWT — element e is (last-column symbol, row) of the e-th real row
+    u32 origin;     // mode 1: origin index of the transform (`text` is the BWT)
 };
 
 // The body of one tile.  FULL = all THREADS*ITEMS slots hold a pair (every tile but the last):
@@ -255,7 +257,20 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
     // so every load instruction of a warp covers 32 consecutive pairs and rank order == index order.
     const u32 local0 = warp * (32 * ITEMS) + lane;
     u64 key[ITEMS];
-    if (GEN) {
+    if (GEN && gen.mode == 1) {
+        // inverse BWT, step 1 (suffix_kernels.cuh): row r(e) = 0, e, or e+1 around the origin; key = that row's last symbol
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const u32 jl = local0 + k * 32;
+            key[k] = ~0ull;
+            if (FULL || jl < nvalid) {
+                const u32 e = (u32)tile_base + jl;
+                const u32 r = e == 0 ? 0u : (e <= gen.origin ? e : e + 1u);
+                key[k] = (u64)__ldg(gen.text + (e == 0 ? gen.origin : r - 1));
+                s.raw_vals[jl] = r;
+            }
+        }
+    } else if (GEN) {
         // the tile's symbol codes, packed MSB-first into 32-bit words (s.keys is free until the re-order);
         // a key is a 64-bit window of that bit stream
         u32* words = reinterpret_cast<u32*>(s.keys);
