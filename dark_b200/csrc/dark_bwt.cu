@@ -933,8 +933,19 @@ int inverse_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, u64 origin64, u8
     const u32 nodes = regular + 1;
     u32* dist[2] = {ctx->ranks, ctx->sa};
     u32* next[2] = {ctx->isa, ctx->ids[cur ^ 1]};
-    k_ibwt_walk<false><<<(u32)ceil_div(nodes, 128), 128, 0, ctx->stream>>>(psi1, n, head, stride, regular, dist[0], next[0], nullptr,
-                                                                           nullptr, nullptr);
+    // one walk: count the sublists and stash their symbols (DARK_BWT_IBWT_TWO_WALKS=1: count, then a second walk writes)
+    static const char* twe = getenv("DARK_BWT_IBWT_TWO_WALKS");
+    u32* len_keep = ctx->ranks_alt;
+    u32* stash = (u32*)ctx->keys[cur ^ 1];  // the sort's other key buffer (8 n + 1024 bytes) is free: nodes * 384 <= 6 n + 768
+    const u32 cap = (u32)std::min<u64>(kIbwtStashCap, (((u64)n * 8 + 1024) / nodes) & ~3ull);  // smaller strides: smaller chunks
+    const bool two_walks = (twe && atoi(twe) != 0) || cap < 8;
+    // k_ibwt_walk needs the symbol bases (exclusive digit counts of pass 0, left in ctx->hist by run_sort)
+    if (two_walks)
+        k_ibwt_walk<0><<<(u32)ceil_div(nodes, 128), 128, 0, ctx->stream>>>(psi1, n, head, stride, regular, dist[0], next[0], nullptr, nullptr,
+                                                                         nullptr, nullptr, nullptr, 0u, 0u);
+    else
+        k_ibwt_walk<2><<<(u32)ceil_div(nodes, 128), 128, 0, ctx->stream>>>(psi1, n, head, stride, regular, dist[0], next[0], nullptr, ctx->hist,
+                                                                         nullptr, len_keep, stash, 0u, cap);
     LAUNCHED();
     // step 3: suffix sums of the sublist lengths along the splitter list (pointer jumping)
     int w = 0;
@@ -951,10 +962,18 @@ int inverse_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, u64 origin64, u8
                  ctx->mail->count, (unsigned long long)n + 1);
         return DARK_BWT_E_INVALID_ARG;
     }
-    // step 4: walk again, writing the text
-    k_ibwt_walk<true><<<(u32)ceil_div(nodes, 128), 128, 0, ctx->stream>>>(psi1, n, head, stride, regular, nullptr, nullptr, dist[w],
-                                                                          ctx->hist, d_text);
-    LAUNCHED();
+    // step 4: the text.  Stashed sublists are copied to their offsets; the few longer ones are walked again.
+    if (two_walks) {
+        k_ibwt_walk<1><<<(u32)ceil_div(nodes, 128), 128, 0, ctx->stream>>>(psi1, n, head, stride, regular, nullptr, nullptr, dist[w], ctx->hist,
+                                                                         d_text, nullptr, nullptr, 0u, 0u);
+        LAUNCHED();
+    } else {
+        k_ibwt_unstash<<<(u32)ceil_div(nodes, 128), 128, 0, ctx->stream>>>(stash, len_keep, dist[w], n, regular, d_text, cap);
+        LAUNCHED();
+        k_ibwt_walk<1><<<(u32)ceil_div(nodes, 128), 128, 0, ctx->stream>>>(psi1, n, head, stride, regular, nullptr, nullptr, dist[w], ctx->hist,
+                                                                         d_text, len_keep, nullptr, cap, 0u);
+        LAUNCHED();
+    }
     CK(cudaEventRecord(eb, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ms_out) cudaEventElapsedTime(ms_out, ea, eb);

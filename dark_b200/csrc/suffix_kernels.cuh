@@ -1213,13 +1213,21 @@ __device__ __forceinline__ u32 ibwt_first_symbol(const u32* s_base, u32 r) {
     return lo;
 }
 
-template <bool WRITE>
+// MODE 0: count only (sublist length + successor splitter).
+// MODE 1: write the text at the known offset (second walk; with `only_longer_than` > 0 just the sublists longer than that).
+// MODE 2: count AND stash the symbols of the sublist in the splitter's private chunk of `stash` (kIbwtStashCap bytes):
+//         the text offset is not known yet, k_ibwt_unstash copies the chunk once it is.  One walk instead of two —
+//         a walk is n dependent random reads of psi and runs at the memory system's transaction rate (~55 G/s).
+constexpr u32 kIbwtStashCap = 384;  // bytes per chunk at the default stride: sublists are ~geometric with mean `stride` = 64,
+                                    // 0.25 % are longer and are walked again (the driver passes min(this, what the buffer allows))
+template <int MODE>
 __global__ void __launch_bounds__(128)
 k_ibwt_walk(const u32* __restrict__ psi1 /* psi[r] for r >= 1 at psi1[r-1] */, u32 n, u32 head, u32 stride, u32 regular,
             u32* __restrict__ len, u32* __restrict__ next, const u32* __restrict__ dist, const u32* __restrict__ base,
-            u8* __restrict__ text_out) {
+            u8* __restrict__ text_out, u32* __restrict__ len_keep, u32* __restrict__ stash, u32 only_longer_than, u32 cap) {
+    constexpr bool WRITE = MODE == 1, COUNT = MODE != 1, STASH = MODE == 2;
     __shared__ u32 s_base[256];
-    if (WRITE) {
+    if (!COUNT || STASH) {
         for (int i = threadIdx.x; i < 256; i += 128) s_base[i] = base[i];
         __syncthreads();
     }
@@ -1227,21 +1235,23 @@ k_ibwt_walk(const u32* __restrict__ psi1 /* psi[r] for r >= 1 at psi1[r-1] */, u
     if (s > regular) return;  // splitters 0..regular-1 are rows s*stride; splitter `regular` is the head row
     u32 r = s < regular ? s * stride : head;
     if (s < regular && r == head) {  // the head row is owned by its own splitter
-        if (!WRITE) {
+        if (COUNT) {
             len[s] = 0;
             next[s] = kIbwtNil;
+            if (STASH) len_keep[s] = 0;
         }
         return;
     }
+    if (WRITE && only_longer_than && len_keep[s] <= only_longer_than) return;
     u64 pos = 0;
     if (WRITE) pos = (u64)(n + 1) - dist[s];  // text position of this splitter's row
     u32 cnt = 0;
     // WRITE: a sublist spells consecutive text positions; the bytes are gathered into aligned 32-bit words and
-    // stored once per word (the walks are bound by the number of memory transactions, ~55 G/s: one random psi
-    // read per step; a byte store per step made the writing walk 9.3 ms against 5.2 ms for the counting one)
+    // stored once per word (a byte store per step made the writing walk 9.3 ms against 5.2 ms for the counting one)
     const bool word_stores = WRITE && (((uintptr_t)text_out) & 3) == 0;
     u32 acc = 0, have = 0;
     u64 wbase = 0;  // text offset of the word being gathered
+    u32* const chunk = STASH ? stash + (size_t)s * (cap / 4) : nullptr;  // cap: chunk bytes, a multiple of 4
     do {
         if (WRITE && r != 0 && pos + cnt < n) {
             const u64 q = pos + cnt;
@@ -1264,6 +1274,14 @@ k_ibwt_walk(const u32* __restrict__ psi1 /* psi[r] for r >= 1 at psi1[r-1] */, u
                 text_out[q] = (u8)sym;
             }
         }
+        if (STASH && cnt < cap) {  // byte cnt of the chunk (row 0, the '$' row, leaves a placeholder)
+            const u32 sym = r != 0 ? ibwt_first_symbol(s_base, r) : 0u;
+            acc |= sym << (8 * (cnt & 3));
+            if ((cnt & 3) == 3) {
+                chunk[cnt >> 2] = acc;
+                acc = 0;
+            }
+        }
         ++cnt;
         r = r == 0 ? head : __ldg(psi1 + (r - 1));
     } while (!(r % stride == 0 || r == head) && cnt <= n);  // cnt bound: corrupt input must not hang
@@ -1271,11 +1289,43 @@ k_ibwt_walk(const u32* __restrict__ psi1 /* psi[r] for r >= 1 at psi1[r-1] */, u
         for (u32 e = 0; e < 4; ++e)
             if ((have >> e) & 1u) text_out[wbase + e] = (u8)(acc >> (8 * e));
     }
-    if (!WRITE) {
+    if (STASH && (cnt & 3) != 0 && cnt < cap) chunk[cnt >> 2] = acc;  // partial last word: the chunk is private
+    if (COUNT) {
         len[s] = cnt;
+        if (STASH) len_keep[s] = cnt;
         // the sublist of row 0 ('$', the last node) ends the list: psi[0] wraps to the head
         next[s] = (s == 0) ? kIbwtNil : (r == head ? regular : r / stride);
     }
+}
+
+// Copy every stashed sublist (length <= kIbwtStashCap) to its place in the text: aligned 32-bit stores composed from
+// two neighbouring chunk words, single bytes only at the two ends.
+__global__ void __launch_bounds__(128)
+k_ibwt_unstash(const u32* __restrict__ stash, const u32* __restrict__ len_keep, const u32* __restrict__ dist, u32 n, u32 regular,
+               u8* __restrict__ text_out, u32 cap) {
+    const u32 s = blockIdx.x * 128 + threadIdx.x;
+    if (s > regular) return;
+    const u32 len = len_keep[s];
+    if (len == 0 || len > cap) return;  // longer sublists are written by a second walk
+    const u64 pos = (u64)(n + 1) - dist[s];
+    if (pos >= n) return;
+    const u32 L = (u32)min((u64)len, (u64)n - pos);  // the '$' row's placeholder falls off the end
+    const u32* src = stash + (size_t)s * (cap / 4);
+    u8* dst = text_out + pos;
+    auto byte_at = [&](u32 i) { return (u8)(src[i >> 2] >> (8 * (i & 3))); };
+    u32 i = 0;
+    if ((((uintptr_t)text_out) & 3) == 0) {
+        while (((pos + i) & 3) != 0 && i < L) {
+            dst[i] = byte_at(i);
+            ++i;
+        }
+        const u32 sh = 8 * (i & 3);  // constant from here on: source and destination differ by a fixed byte offset
+        for (; i + 4 <= L; i += 4) {
+            const u32 lo = src[i >> 2], hi = sh ? src[(i >> 2) + 1] : 0u;  // (the word after the last is inside the chunk or unused)
+            *reinterpret_cast<u32*>(dst + i) = sh ? __funnelshift_r(lo, hi, sh) : lo;
+        }
+    }
+    for (; i < L; ++i) dst[i] = byte_at(i);
 }
 
 __global__ void k_ibwt_report(const u32* __restrict__ dist, u32 head_splitter, u32* __restrict__ out) { *out = dist[head_splitter]; }

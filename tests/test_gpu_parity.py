@@ -628,3 +628,25 @@ def test_many_blocks_rejects_bad_arguments(saca, torch):
         with pytest.raises(_ffi.DarkBwtError):
             con.bwt_many([b"a" * 600, b"b" * 600])  # the blocks share one arena: 1200 > capacity
         assert con.bwt_many([]) == []
+
+
+@pytest.mark.parametrize("env_extra", [{"DARK_BWT_IBWT_TWO_WALKS": "1"}, {"DARK_BWT_IBWT_STRIDE": "1024"},
+                                       {"DARK_BWT_IBWT_STRIDE": "400"}, {"DARK_BWT_IBWT_STRIDE": "2"}])
+def test_inverse_forced_paths(env_extra):
+    """The two-walk variant, and splitter strides that make most sublists longer than the stash chunk (they are then
+    written by the second, selective walk) or as short as possible."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, oracle\n"
+        "from dark_b200 import saca, synth\n"
+        "for kind, seed, n in (('mixed', 4, 700001), ('dna', 2, 300007), ('rep17', 2, 200003), ('text', 3, 5)):\n"
+        "    t = synth.generate(kind, seed, n)\n"
+        "    b, o = oracle.bwt_forward(t)\n"
+        "    with saca.Constructor(n) as c:\n"
+        "        assert np.array_equal(c.inverse(b, o), t), (kind, n)\n"
+        "print('ok')\n")
+    env = dict(os.environ, **env_extra)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
