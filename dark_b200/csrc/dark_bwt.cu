@@ -927,7 +927,7 @@ int inverse_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, u64 origin64, u8
     const u32* psi1 = ctx->ids[cur];
     // step 2: sublists between splitters
     const char* se = getenv("DARK_BWT_IBWT_STRIDE");  // rows between splitters (sweeps only)
-    const u32 stride = se ? (u32)std::max(2, atoi(se)) : 64u;
+    const u32 stride = se ? (u32)std::max(2, atoi(se)) : 48u;  // swept 24..128 with the single walk: 48 (profiles/r1_final.md)
     const u32 head = origin + 1;
     const u32 regular = (u32)ceil_div((u64)n + 1, stride);
     const u32 nodes = regular + 1;

@@ -1218,8 +1218,8 @@ __device__ __forceinline__ u32 ibwt_first_symbol(const u32* s_base, u32 r) {
 // MODE 2: count AND stash the symbols of the sublist in the splitter's private chunk of `stash` (kIbwtStashCap bytes):
 //         the text offset is not known yet, k_ibwt_unstash copies the chunk once it is.  One walk instead of two —
 //         a walk is n dependent random reads of psi and runs at the memory system's transaction rate (~55 G/s).
-constexpr u32 kIbwtStashCap = 384;  // bytes per chunk at the default stride: sublists are ~geometric with mean `stride` = 64,
-                                    // 0.25 % are longer and are walked again (the driver passes min(this, what the buffer allows))
+constexpr u32 kIbwtStashCap = 384;  // bytes per chunk at the default stride: sublists are ~geometric with mean `stride` (48 by default),
+                                    // 0.03 % are longer and are walked again (the driver passes min(this, what the buffer allows))
 template <int MODE>
 __global__ void __launch_bounds__(128)
 k_ibwt_walk(const u32* __restrict__ psi1 /* psi[r] for r >= 1 at psi1[r-1] */, u32 n, u32 head, u32 stride, u32 regular,
