@@ -517,6 +517,10 @@ constexpr int kScanWordsPerTile = 4;
 #ifndef DARK_LB_WARPS
 #define DARK_LB_WARPS 4
 #endif
+#ifndef DARK_RERANK_DEFER
+#define DARK_RERANK_DEFER 1
+#endif
+constexpr bool kRerankDeferLoads = DARK_RERANK_DEFER != 0;  // rounds >= 1: ids and old ranks are loaded after the publish
 constexpr int kLookbackWarps = DARK_LB_WARPS;  // 32 x this many predecessor tiles polled per look-back step
 __device__ __forceinline__ u64 scan_pack(u32 flag, u32 value) { return ((u64)flag << 62) | value; }
 
@@ -585,20 +589,22 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
             key[1 + 2 * k] = q.x;
             key[2 + 2 * k] = q.y;
         }
-        const uint4* iv = reinterpret_cast<const uint4*>(ids + p0);
+        if (ROUND0 || !kRerankDeferLoads) {
+            const uint4* iv = reinterpret_cast<const uint4*>(ids + p0);
 #pragma unroll
-        for (int k = 0; k < ITEMS / 4; ++k) {
-            const uint4 q = iv[k];
-            id[1 + 4 * k] = q.x;
-            id[2 + 4 * k] = q.y;
-            id[3 + 4 * k] = q.z;
-            id[4 + 4 * k] = q.w;
+            for (int k = 0; k < ITEMS / 4; ++k) {
+                const uint4 q = iv[k];
+                id[1 + 4 * k] = q.x;
+                id[2 + 4 * k] = q.y;
+                id[3 + 4 * k] = q.z;
+                id[4 + 4 * k] = q.w;
+            }
         }
     } else {
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
             key[1 + k] = (p0 + k < m) ? keys[p0 + k] : 0;
-            id[1 + k] = (p0 + k < m) ? ids[p0 + k] : 0;
+            if (ROUND0 || !kRerankDeferLoads) id[1 + k] = (p0 + k < m) ? ids[p0 + k] : 0;
         }
     }
     key[0] = (p0 > 0 && p0 - 1 < m) ? keys[p0 - 1] : 0;
@@ -614,7 +620,39 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     // rank comes from the list itself: sorting permutes elements only inside their group, and every
     // member of a group holds the same rank, so ranks_in[p] is the rank of whatever lands at index p.
     u32 rold[ITEMS];
-    if (!ROUND0) {
+    // Rounds >= 1: the head flags need the keys only.  The ids and the old ranks are fetched AFTER the tile's
+    // aggregate is on its way (below), so that fewer bytes stand between a tile's start and its publish — every later
+    // tile's look-back waits for the slowest recent tile to publish (profiles/r1_ncu_rerank_final.md) — and their
+    // latency hides behind the look-back.
+    auto load_ids_and_ranks = [&]() {
+        if (p0 + ITEMS <= m) {
+            const uint4* iv = reinterpret_cast<const uint4*>(ids + p0);
+#pragma unroll
+            for (int k = 0; k < ITEMS / 4; ++k) {
+                const uint4 q = iv[k];
+                id[1 + 4 * k] = q.x;
+                id[2 + 4 * k] = q.y;
+                id[3 + 4 * k] = q.z;
+                id[4 + 4 * k] = q.w;
+            }
+            const uint4* rv = reinterpret_cast<const uint4*>(ranks_in + p0);
+#pragma unroll
+            for (int k = 0; k < ITEMS / 4; ++k) {
+                const uint4 q = rv[k];
+                rold[4 * k] = q.x;
+                rold[4 * k + 1] = q.y;
+                rold[4 * k + 2] = q.z;
+                rold[4 * k + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                id[1 + k] = (p0 + k < m) ? ids[p0 + k] : 0u;
+                rold[k] = (p0 + k < m) ? ranks_in[p0 + k] : 0u;
+            }
+        }
+    };
+    if (!ROUND0 && !kRerankDeferLoads) {
         if (p0 + ITEMS <= m) {
             const uint4* rv = reinterpret_cast<const uint4*>(ranks_in + p0);
 #pragma unroll
@@ -684,6 +722,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
+    if (!ROUND0 && kRerankDeferLoads) load_ids_and_ranks();
     ScanTriple wprefix = {0u, 0u, 0u};
     for (int w = 0; w < warp; ++w) wprefix = scan_combine(wprefix, s_warp[w]);
     ScanTriple texcl = shfl_up_triple(incl, 1);
