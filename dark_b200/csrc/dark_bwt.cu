@@ -191,8 +191,13 @@ int launch_pass_kernel(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* k
     const u32 knock = ke ? (u32)atoi(ke) : 0u;
     // persistent grid: as many CTAs as stay resident (SMs x MINBLOCKS), each claiming tiles until none are left
     const u32 grid = by_block_index ? tiles : std::min<u32>(tiles, (u32)ctx->num_sms * MINBLOCKS);
+    // L2 prefetch distance in tiles: two thirds of a wave of claims (the persistent grid; 148..444 measured alike, beyond
+    // one wave the gain fades) unless DARK_BWT_PASS_PREFETCH says otherwise (0 = off)
+    static const char* ppe = getenv("DARK_BWT_PASS_PREFETCH");
+    const u32 prefetch_ahead = by_block_index ? 0u : (ppe ? (u32)atoi(ppe) : std::max(1u, grid * 2 / 3));
     kern<<<grid, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base, (StatusT*)ctx->sort_status,
-                                                        by_block_index ? nullptr : counter, ctx->pass_trace, prev_text, n_text, knock, gen);
+                                                        by_block_index ? nullptr : counter, ctx->pass_trace, prev_text, n_text, knock, gen,
+                                                        prefetch_ahead);
     LAUNCHED();
     return 0;
 }
@@ -326,7 +331,7 @@ int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32
     CK(cudaMemsetAsync(ctx->scan_words, 0, sizeof(u64) * kScanWordsPerTile * tiles, ctx->stream));
     ScanTileState ts{ctx->scan_words};
     static const char* pfe = getenv("DARK_BWT_RERANK_PREFETCH");
-    const u32 prefetch_ahead = pfe ? (u32)atoi(pfe) : 0u;
+    const u32 prefetch_ahead = pfe ? (u32)atoi(pfe) : 2u * (u32)ctx->num_sms;  // one wave of CTAs ahead (-2 %)
     auto kern = k_rerank<kScanThreads, kScanItems, ROUND0, PAIRS>;
     constexpr size_t smem = (size_t)kScanTile * 8;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
