@@ -58,6 +58,19 @@ def test_stats_struct_layout_matches_header():
     assert vals[1:] == [getattr(_ffi.Stats, f).offset for f in fields]
 
 
+def test_null_arguments_are_rejected_before_any_device_work(lib):
+    """Argument checks of the entry points run before anything touches CUDA: DARK_BWT_E_INVALID_ARG (2), no crash."""
+    from dark_b200 import _ffi
+    o = ctypes.c_uint64(0)
+    assert lib.dark_bwt_forward(None, None, 10, None, ctypes.byref(o), None, None) == _ffi.E_INVALID_ARG
+    assert lib.dark_bwt_forward_device(None, None, 10, None, ctypes.byref(o), None, None) == _ffi.E_INVALID_ARG
+    assert lib.dark_bwt_forward_batch(None, None, None, None, None, None, 3, None) == _ffi.E_INVALID_ARG
+    assert lib.dark_bwt_forward_many(None, None, None, None, None, 3, None) == _ffi.E_INVALID_ARG
+    assert lib.dark_bwt_forward_many_device(None, None, None, 3, None, None, None, None) == _ffi.E_INVALID_ARG
+    assert lib.dark_bwt_capacity(None) == 0
+    lib.dark_bwt_destroy(None)
+
+
 def test_no_cpu_fallback_create_fails_without_gpu(lib):
     """On a box without a CUDA device the product path must fail loudly."""
     import torch
