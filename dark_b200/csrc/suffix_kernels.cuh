@@ -324,6 +324,13 @@ k_build_keys_text(const u32* __restrict__ isa, u32 n, u64 h, int kb, u32 tag, u6
         __syncthreads();
         const u32 tile = s_tile;
         if (tile >= ntiles) break;
+        {   // L2 prefetch of the tile this CTA is likely to claim next, both streams (as in the radix pass)
+            const u64 q = ((u64)tile + (gridDim.x * 2u) / 3u) * TILE;
+            if (q + TILE <= n && tid < TILE / 32) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(isa + q + (u64)tid * 32));
+                if (q + h + TILE <= n) asm volatile("prefetch.global.L2 [%0];" ::"l"(isa + q + h + (u64)tid * 32));
+            }
+        }
         const u64 i0 = (u64)tile * TILE + (u64)tid * ITEMS;  // blocked: a thread owns ITEMS consecutive suffixes
         u32 r1[ITEMS], r2[ITEMS];
         if (i0 + ITEMS <= n) {
