@@ -63,6 +63,25 @@ public:
         return {p, (size_t)cnt};
     }
 
+    // Many small blocks in one pass over the GPU (dark_bwt_forward_many): (bwt, origin) per block, each identical to
+    // bwt(block).  The blocks share the arena: their lengths must sum to <= capacity().
+    std::vector<std::pair<std::vector<Symbol>, size_t>> bwt_many(const std::vector<std::pair<const Symbol*, size_t>>& blocks) {
+        const size_t cnt = blocks.size();
+        std::vector<std::pair<std::vector<Symbol>, size_t>> res(cnt);
+        std::vector<const uint8_t*> texts(cnt);
+        std::vector<uint64_t> ns(cnt), origins(cnt);
+        std::vector<uint8_t*> outs(cnt);
+        for (size_t k = 0; k < cnt; ++k) {
+            texts[k] = blocks[k].first;
+            ns[k] = blocks[k].second;
+            res[k].first.resize(blocks[k].second);
+            outs[k] = res[k].first.data();
+        }
+        check(dark_bwt_forward_many(ctx_, texts.data(), ns.data(), outs.data(), origins.data(), cnt, &stats_), "Constructor::bwt_many");
+        for (size_t k = 0; k < cnt; ++k) res[k].second = (size_t)origins[k];
+        return res;
+    }
+
     const dark_bwt_stats& stats() const { return stats_; }
     dark_bwt_ctx* raw() { return ctx_; }
 

@@ -33,6 +33,12 @@ int main() {
         if (rc) return rc;
         rc = check("banana", {5, 3, 1, 0, 4, 2}, 3, "nnbaaa");
         if (rc) return 10 + rc;
+        {  // both known answers again, as two blocks sorted in one pass (dark_bwt_forward_many)
+            dark::saca::Constructor many(64);
+            auto res = many.bwt_many({{reinterpret_cast<const uint8_t*>("abracadabra"), 11}, {reinterpret_cast<const uint8_t*>("banana"), 6}});
+            if (res.size() != 2 || res[0].second != 2 || res[1].second != 3) return 30;
+            if (memcmp(res[0].first.data(), "rdarcaaaabb", 11) != 0 || memcmp(res[1].first.data(), "nnbaaa", 6) != 0) return 31;
+        }
         try {  // n == 1 panics in the reference (saca.rs:300): the mirror throws
             dark::saca::Constructor one(2);
             one.bwt(reinterpret_cast<const uint8_t*>("x"), 1);
