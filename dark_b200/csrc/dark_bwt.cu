@@ -575,11 +575,54 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     const int passes_r = (key_bits + kRadixBits - 1) / kRadixBits;
 
     sp = span_begin(ctx, PH_RERANK);
-    if (int rc = launch_rerank<true, false>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, Kc, drop, sa, ctx->ids[cur ^ 1], d_text, bwt_inline)) return rc;
+    u32 m = 0;
+    bool sparse_done = false;
+    // Pruned initial sort with inline emission (high-entropy block: almost everything settles): the chain-free
+    // sparse re-rank (suffix_kernels.cuh).  DARK_BWT_SPARSE_RERANK=0 keeps the scan-based kernel.
+    static const char* spe = getenv("DARK_BWT_SPARSE_RERANK");
+    if (emit_inline && first_pass >= 1 && (spe ? atoi(spe) != 0 : true)) {
+        u32 *total = nullptr, *ovf = nullptr;
+        if (int rc = next_counter(ctx, &total)) return rc;
+        if (int rc = next_counter(ctx, &ovf)) return rc;
+        const u32 tiles = (u32)ceil_div(n, kScanTile);
+        k_rerank0_sparse<kScanThreads, kScanItems><<<tiles, kScanThreads, 0, ctx->stream>>>(
+            ctx->keys[cur], ctx->ids[cur], n, Kc, drop, sa, bwt_inline, &ctx->mail_dev->origin, (u8*)ctx->bitmap, total);
+        LAUNCHED();
+        k_copy_u32<<<1, 1, 0, ctx->stream>>>(total, &ctx->mail_dev->count);
+        LAUNCHED();
+        u32 survivors = 0;
+        if (int rc = fetch_count(ctx, &survivors)) return rc;
+        if (survivors == 0) {
+            sparse_done = true;
+        } else if (survivors <= n / 16) {
+            const u64 nbytes = ceil_div(n, 8);
+            const u32 nblocks = (u32)ceil_div(nbytes, kSparseChunk);
+            u32* counts = (u32*)ctx->scan_words;  // n/32768 counters; the scan state is not in use
+            u32* pos = ctx->ranks_alt;
+            k_sparse_count<<<nblocks, 256, 0, ctx->stream>>>((const u8*)ctx->bitmap, nbytes, counts);
+            LAUNCHED();
+            k_sparse_scan<<<1, 1024, 0, ctx->stream>>>(counts, nblocks);
+            LAUNCHED();
+            k_sparse_positions<<<nblocks, 256, 0, ctx->stream>>>((const u8*)ctx->bitmap, nbytes, counts, pos);
+            LAUNCHED();
+            k_sparse_finalize<<<(u32)ceil_div(survivors, 256), 256, 0, ctx->stream>>>(pos, survivors, ctx->keys[cur], ctx->ids[cur], n, Kc, drop,
+                                                                                 ctx->ids[cur ^ 1], ctx->ranks, ovf);
+            LAUNCHED();
+            k_copy_u32<<<1, 1, 0, ctx->stream>>>(ovf, &ctx->mail_dev->flag);
+            LAUNCHED();
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->mail->flag == 0) {
+                sparse_done = true;
+                m = survivors;
+            }
+        }
+    }
+    if (!sparse_done) {
+        if (int rc = launch_rerank<true, false>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, Kc, drop, sa, ctx->ids[cur ^ 1], d_text, bwt_inline)) return rc;
+        if (int rc = fetch_count(ctx, &m)) return rc;
+    }
     span_end(ctx, sp);
     cur ^= 1;  // the compacted active ids now live in ids[cur]
-    u32 m = 0;
-    if (int rc = fetch_count(ctx, &m)) return rc;
 
     // Round 0 wrote no ranks.  If a round follows they are needed: all of them when many suffixes
     // survive; otherwise only the survivors' now, and per round the few that are actually read.

@@ -956,6 +956,208 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     }
 }
 
+// ---- sparse round-0 re-rank (pruned initial sort: almost every suffix settles) -------------------------------
+// After a pruned round 0 of a high-entropy block (C2: 65,792 survivors of 2^28) the scan of k_rerank carries almost
+// nothing, yet its look-back chain sets the kernel's pace (1.66 ms per 2^28 against 0.8 ms of memory time,
+// profiles/r1_ncu_rerank_final.md).  What a SETTLED suffix writes depends on its own head flags only, so the tiles
+// run without any chain: k_rerank0_sparse writes the SA slots and BWT bytes of the singletons and one survivor bit
+// per slot; the few survivors are then listed in slot order from the bitmap (count / scan / positions) and each
+// finds its group head by walking left over equal keys (k_sparse_finalize).  The driver falls back to k_rerank when
+// more than n/16 suffixes survive or a group turns out longer than kSparseMaxWalk.
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+k_rerank0_sparse(const u64* __restrict__ keys, const u32* __restrict__ ids, u32 n, int K, int kb, u32* __restrict__ sa,
+                 u8* __restrict__ bwt_inline, u64* __restrict__ origin, u8* __restrict__ surv_bits, u32* __restrict__ surv_total) {
+    static_assert(ITEMS == 8, "one survivor byte and two 128-bit SA stores per thread");
+    constexpr int TILE = THREADS * ITEMS;
+    const int tid = threadIdx.x;
+    const u32 m = n;
+    const u64 p0 = (u64)blockIdx.x * TILE + (u64)tid * ITEMS;
+    if (p0 >= m) return;
+    u64 key[ITEMS + 2];
+    u32 id[ITEMS + 2];
+    if (p0 + ITEMS <= m) {
+        const ulonglong2* kv = reinterpret_cast<const ulonglong2*>(keys + p0);
+#pragma unroll
+        for (int k = 0; k < ITEMS / 2; ++k) {
+            const ulonglong2 q = kv[k];
+            key[1 + 2 * k] = q.x;
+            key[2 + 2 * k] = q.y;
+        }
+        const uint4* iv = reinterpret_cast<const uint4*>(ids + p0);
+#pragma unroll
+        for (int k = 0; k < ITEMS / 4; ++k) {
+            const uint4 q = iv[k];
+            id[1 + 4 * k] = q.x;
+            id[2 + 4 * k] = q.y;
+            id[3 + 4 * k] = q.z;
+            id[4 + 4 * k] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            key[1 + k] = (p0 + k < m) ? keys[p0 + k] : 0;
+            id[1 + k] = (p0 + k < m) ? ids[p0 + k] : 0;
+        }
+    }
+    key[0] = p0 > 0 ? keys[p0 - 1] : 0;
+    key[ITEMS + 1] = (p0 + ITEMS < m) ? keys[p0 + ITEMS] : 0;
+    id[0] = p0 > 0 ? ids[p0 - 1] : 0;
+    id[ITEMS + 1] = (p0 + ITEMS < m) ? ids[p0 + ITEMS] : 0;
+    // head flags exactly as k_rerank<ROUND0> computes them
+    const u32 short_from = n >= (u32)K ? n - (u32)K + 1u : 0u;
+    const u32 navail = (u32)min((u64)ITEMS + 1, (u64)m - p0);
+    const u32 nvalid = min(navail, (u32)ITEMS);
+    u32 newh = 0;
+#pragma unroll
+    for (int k = 0; k <= ITEMS; ++k) {
+        const bool nh = (key[k + 1] >> kb) != (key[k] >> kb) || id[k + 1] >= short_from || id[k] >= short_from;
+        newh |= (nh ? 1u : 0u) << k;
+    }
+    if (p0 == 0) newh |= 1u;
+    if (navail < (u32)ITEMS + 1u) newh |= ~((1u << navail) - 1u) & ((2u << ITEMS) - 1u);
+    const u32 vmask = (1u << nvalid) - 1u;
+    const u32 singles = newh & (newh >> 1) & vmask;
+    u32 v_sa[ITEMS];
+    u32 v_b0 = 0, v_b1 = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const bool single = (singles >> k) & 1u;
+        v_sa[k] = single ? id[k + 1] : 0xFFFFFFFFu;
+        if (single) {
+            const u32 byte = (u32)key[k + 1] & 0xFFu;
+            if (k < 4) v_b0 |= byte << (8 * k);
+            else v_b1 |= byte << (8 * (k - 4));
+            if (id[k + 1] == 0) *origin = p0 + k;
+        }
+    }
+    if (p0 + ITEMS <= m && (((uintptr_t)sa) & 15) == 0) {
+        uint4* o = reinterpret_cast<uint4*>(sa + p0);
+        o[0] = make_uint4(v_sa[0], v_sa[1], v_sa[2], v_sa[3]);
+        o[1] = make_uint4(v_sa[4], v_sa[5], v_sa[6], v_sa[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k)
+            if (p0 + k < m) sa[p0 + k] = v_sa[k];
+    }
+    if (p0 + ITEMS <= m && (((uintptr_t)bwt_inline) & 7) == 0) {
+        *reinterpret_cast<uint2*>(bwt_inline + p0) = make_uint2(v_b0, v_b1);
+    } else {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k)
+            if (p0 + k < m) bwt_inline[p0 + k] = (u8)((k < 4 ? v_b0 >> (8 * k) : v_b1 >> (8 * (k - 4))) & 0xFFu);
+    }
+    const u32 surv = ~singles & vmask;
+    surv_bits[p0 >> 3] = (u8)surv;
+    if (surv) atomicAdd(surv_total, (u32)__popc(surv));
+}
+
+constexpr u32 kSparseChunk = 4096;   // bitmap bytes per CTA of the compaction kernels (256 threads x 16 bytes)
+constexpr u32 kSparseMaxWalk = 64;   // longest group the sparse path resolves itself
+__device__ __forceinline__ uint4 sparse_load16(const u8* __restrict__ bits, u64 nbytes, u64 c0) {
+    if (c0 + 16 <= nbytes) return *reinterpret_cast<const uint4*>(bits + c0);
+    u32 w[4] = {0u, 0u, 0u, 0u};
+    for (u32 e = 0; e < 16; ++e)
+        if (c0 + e < nbytes) w[e >> 2] |= (u32)bits[c0 + e] << (8 * (e & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__global__ void __launch_bounds__(256) k_sparse_count(const u8* __restrict__ bits, u64 nbytes, u32* __restrict__ counts) {
+    __shared__ u32 s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const u64 c0 = (u64)blockIdx.x * kSparseChunk + (u64)threadIdx.x * 16;
+    u32 c = 0;
+    if (c0 < nbytes) {
+        const uint4 v = sparse_load16(bits, nbytes, c0);
+        c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_sum, c);
+    __syncthreads();
+    if (threadIdx.x == 0) counts[blockIdx.x] = s_sum;
+}
+__global__ void __launch_bounds__(1024) k_sparse_scan(u32* __restrict__ counts, u32 nblocks) {  // in place: exclusive offsets
+    __shared__ u32 s_warp[32];
+    __shared__ u32 s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (u32 b0 = 0; b0 < nblocks; b0 += 1024) {
+        const u32 i = b0 + tid;
+        const u32 c = i < nblocks ? counts[i] : 0u;
+        u32 incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        u32 wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+        const u32 carry = s_carry;
+        if (i < nblocks) counts[i] = carry + wbase + incl - c;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + wbase + incl;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256)
+k_sparse_positions(const u8* __restrict__ bits, u64 nbytes, const u32* __restrict__ offsets, u32* __restrict__ pos_out) {
+    __shared__ u32 s_warp[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 c0 = (u64)blockIdx.x * kSparseChunk + (u64)tid * 16;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (c0 < nbytes) v = sparse_load16(bits, nbytes, c0);
+    const u32 c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    u32 incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    u32 wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+    u32 out = offsets[blockIdx.x] + wbase + incl - c;
+    const u32 w4[4] = {v.x, v.y, v.z, v.w};
+    const u64 bit0 = c0 * 8;  // slot of bit 0 of this thread's first byte
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        u32 word = w4[q];
+        while (word) {
+            const int b = __ffs(word) - 1;
+            word &= word - 1;
+            pos_out[out++] = (u32)(bit0 + 32 * q + b);
+        }
+    }
+}
+// survivor j sits at slot pos[j]; its rank is the slot of its group's head: walk left while the key prefix stays equal
+__global__ void __launch_bounds__(256)
+k_sparse_finalize(const u32* __restrict__ pos, u32 count, const u64* __restrict__ keys, const u32* __restrict__ ids, u32 n, int K, int kb,
+                  u32* __restrict__ out_ids, u32* __restrict__ out_ranks, u32* __restrict__ overflow) {
+    const u32 j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= count) return;
+    const u32 short_from = n >= (u32)K ? n - (u32)K + 1u : 0u;
+    const u32 p = pos[j];
+    const u32 id = ids[p];
+    const u64 hk = keys[p] >> kb;
+    u32 q = p, steps = 0;
+    // slot q is not a head iff slot q-1 has the same key prefix and neither suffix is short (k_rerank<ROUND0>)
+    while (q > 0 && id < short_from) {
+        if ((keys[q - 1] >> kb) != hk || ids[q - 1] >= short_from) break;
+        --q;
+        if (++steps > kSparseMaxWalk) {
+            *overflow = 1;
+            break;
+        }
+    }
+    out_ids[j] = id;
+    out_ranks[j] = q;
+}
+__global__ void k_copy_u32(const u32* __restrict__ src, u32* __restrict__ dst) { *dst = *src; }
+
 // Deferred rank scatter of round 0 (only launched when suffixes survive round 0):
 // settled slots give isa[SA[p]] = p, survivors give isa[id] = rank of their group.
 template <int THREADS>

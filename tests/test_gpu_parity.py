@@ -168,6 +168,7 @@ FORCED_PATHS = [
     ({"DARK_BWT_SORT_VARIANT": "5"}, "dna", 1, 700001),
     ({"DARK_BWT_TILE_BY_BLOCKIDX": "1"}, "mixed", 9, 900001),
     ({"DARK_BWT_RANK_SEARCH": "0"}, "dna", 6, 1500003),              # selective rank fill (bitmap + SA sweep) instead of the search
+    ({"DARK_BWT_SPARSE_RERANK": "0"}, "dna", 9, 1400003),            # pruned round 0 re-ranked by the scan kernel instead of the sparse path
     ({"DARK_BWT_PAIRS": "0"}, "mixed", 4, 1300001),
     ({"DARK_BWT_TEXT_BUILD": "0"}, "mixed", 4, 1100001),             # rank gathers only, isa[] untagged
     ({"DARK_BWT_TEXT_BUILD": "0"}, "rep17", 2, 700001),
@@ -650,3 +651,22 @@ def test_inverse_forced_paths(env_extra):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_sparse_rerank_fallbacks(saca, oracle, torch):
+    """Pruned round 0 (uniform DNA digits) whose survivors defeat the sparse re-rank: a motif planted 150 times (groups
+    longer than the walk limit -> scan kernel), and a block whose second half repeats the first (more than n/16
+    survivors -> scan kernel).  Both must still give the oracle's bytes."""
+    rng = np.random.default_rng(21)
+    a = (rng.integers(0, 4, 1_500_000).astype(np.uint8) + 65)
+    motif = (rng.integers(0, 4, 300).astype(np.uint8) + 65)
+    for k in range(150):
+        a[5000 + 9000 * k: 5000 + 9000 * k + 300] = motif
+    half = (rng.integers(0, 4, 600_000).astype(np.uint8) + 65)
+    b = np.concatenate([half, half])
+    for t in (a, b):
+        bwt_o, origin_o, sa_o = oracle.bwt_forward(t, want_sa=True)
+        with saca.Constructor(t.size) as con:
+            bwt, origin, sa = con.bwt_and_sa(t)
+            assert con.stats.initial_symbols < con.stats.symbols_per_key  # the initial sort was pruned
+        assert origin == origin_o and np.array_equal(sa, sa_o) and np.array_equal(bwt, bwt_o)
