@@ -21,6 +21,7 @@
 #include "../../include/dark_bwt.h"
 #include "common.cuh"
 #include "radix_sort.cuh"
+#include "onesweep_tma.cuh"
 #include "suffix_kernels.cuh"
 
 using namespace dark;
@@ -38,7 +39,7 @@ constexpr int kInitThreads = 256;
 constexpr int kInitItems = 16;
 constexpr int kBuildThreads = 256;
 constexpr int kBuildItems = 8;
-constexpr int kMaxCounters = 1024;
+constexpr int kMaxCounters = 4096;
 constexpr u32 kMaxManyBlocks = DARK_BWT_MAX_MANY_BLOCKS;
 constexpr int kMaxEvents = 16 + 10 * DARK_BWT_MAX_ROUNDS;
 
@@ -225,6 +226,39 @@ int launch_pass_variant(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* 
 #undef LP
 }
 
+// The TMA-staged, software-pipelined pass (onesweep_tma.cuh): byte-aligned digits, 16-byte aligned inputs, plain or
+// key-generating (GEN mode 0).  Returns 1 if this pass is not eligible (the caller then runs k_onesweep_pass).
+template <int THREADS, int ITEMS, int MINBLOCKS, int ILP>
+int launch_pass_tma(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u32* vout, u32 m, int shift, const u32* digit_base,
+                    u32* counter, bool wide, const u8* prev_text, const KeyGen* gen) {
+    typedef PipeSmem<THREADS, ITEMS> Smem;
+    const u32 tiles = (u32)ceil_div(m, Smem::kTile);
+    const size_t bytes = ((size_t)tiles + 3 * kScannerBatch) * kRadix * (wide ? sizeof(u64) : sizeof(u32));  // the scanner reads ahead
+    if (bytes > ctx->sort_status_bytes) return ctx->fail_internal("sort status buffer too small");
+    CK(cudaMemsetAsync(ctx->sort_status, 0, bytes, ctx->stream));
+    const u32 grid = std::min<u32>(tiles + kScanners, (u32)ctx->num_sms * MINBLOCKS);  // kScanners CTAs scan, the rest sort
+    const KeyGen g = gen ? *gen : KeyGen();
+    const bool hi = shift >= 32;
+#define LT(ST, GEN)                                                                                                          \
+    do {                                                                                                                     \
+        auto kern = hi ? k_onesweep_tma<THREADS, ITEMS, MINBLOCKS, ILP, ST, GEN, true>                                       \
+                       : k_onesweep_tma<THREADS, ITEMS, MINBLOCKS, ILP, ST, GEN, false>;                                     \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));                      \
+        kern<<<grid, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base, (ST*)ctx->sort_status, \
+                                                           counter, g, prev_text, ctx->pass_trace);                          \
+    } while (0)
+    if (gen) {
+        if (wide) LT(u64, true);
+        else LT(u32, true);
+    } else {
+        if (wide) LT(u64, false);
+        else LT(u32, false);
+    }
+#undef LT
+    LAUNCHED();
+    return 0;
+}
+
 constexpr int kDefaultSortVariant = 1;  // 256 threads x 16 items, 3 CTAs/SM: best of the sweeps in profiles/r1_sort_variants_*.log
 
 // One onesweep pass over m pairs: buffers[cur] -> buffers[cur^1].
@@ -232,11 +266,25 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
                 const u32* digit_base, const u8* prev_text = nullptr, u32 n_text = 0, const KeyGen* gen = nullptr) {
     u32* counter = nullptr;
     if (int rc = next_counter(ctx, &counter)) return rc;
+    for (int k = 0; k < kScanners; ++k) {
+        u32* scanner_sm = nullptr;  // the words after the tile counter: where the scanner CTAs of onesweep_tma.cuh say which SMs they run on
+        if (int rc = next_counter(ctx, &scanner_sm)) return rc;
+    }
     // 32-bit status words hold prefixes below 2^30; larger sorts (2 GiB blocks) use 64-bit words.
     // DARK_BWT_FORCE_U64_STATUS=1 exercises the wide path on small inputs (tests).
     const bool wide = !(m < (1u << 30)) || getenv("DARK_BWT_FORCE_U64_STATUS") != nullptr;
     const char* ev = getenv("DARK_BWT_SORT_VARIANT");
     const int variant = ev ? atoi(ev) : kDefaultSortVariant;
+    {
+        // default: the TMA-staged pipelined pass; DARK_BWT_PASS_IMPL=0 keeps the round-1 kernel (k_onesweep_pass)
+        const char* pie = getenv("DARK_BWT_PASS_IMPL");
+        const int impl = pie ? atoi(pie) : 1;
+        const bool eligible = (shift & 7) == 0 && ev == nullptr && (gen == nullptr || gen->mode == 0) &&
+                              (gen != nullptr || (prev_text == nullptr && ((uintptr_t)kin & 15) == 0 && ((uintptr_t)vin & 15) == 0));
+        if (impl != 0 && eligible) {
+            return launch_pass_tma<256, 16, 2, 2>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, gen);
+        }
+    }
     if (gen != nullptr) return launch_pass_variant<256, 16, 3, 2>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, n_text, gen);
 #define V(T, I, B, L) return launch_pass_variant<T, I, B, L>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, n_text)
     switch (variant) {
@@ -1077,7 +1125,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
 
     const size_t N = (size_t)max_n;
     const size_t sort_tiles = ceil_div(N, kSortTile);
-    ctx->sort_status_bytes = sort_tiles * kRadix * sizeof(u64);
+    ctx->sort_status_bytes = (sort_tiles + 128) * kRadix * sizeof(u64);  // + rows the scanner CTA reads ahead
     ctx->scan_tiles = ceil_div(N, std::min(kScanTile, 4096));  // the pairs kernel and the text-order builder scan 4,096-suffix tiles
     const bool staging = !(flags & DARK_BWT_F_DEVICE_ONLY);
 

@@ -11,7 +11,7 @@ import torch  # noqa: E402
 from dark_b200 import saca, _ffi  # noqa: E402
 
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 27
-variants = [int(v) for v in sys.argv[2:]] or [0, 1, 2, 3, 4, 5, 6, 7]
+variants = sys.argv[2:] or ["tma", "r1"]   # "tma" = onesweep_tma.cuh (default), "r1" = round-1 kernel, <int> = its tuning variants
 m = 1 << lg
 g = torch.Generator(device="cuda").manual_seed(1)
 keys0 = torch.randint(0, 1 << 62, (m,), dtype=torch.int64, device="cuda", generator=g)
@@ -29,7 +29,12 @@ if m <= (1 << 27):
     ref_vals = ri.to(torch.int32)
     del rk, ri
 for v in variants:
-    os.environ["DARK_BWT_SORT_VARIANT"] = str(v)
+    os.environ.pop("DARK_BWT_SORT_VARIANT", None)
+    os.environ.pop("DARK_BWT_PASS_IMPL", None)
+    if v == "r1":
+        os.environ["DARK_BWT_PASS_IMPL"] = "0"
+    elif v != "tma":
+        os.environ["DARK_BWT_SORT_VARIANT"] = str(int(v))
     best = None
     ok = True
     for rep in range(3):
