@@ -32,6 +32,8 @@ class Stats(ctypes.Structure):
         ("device_ms", ctypes.c_float), ("init_ms", ctypes.c_float), ("sort_ms", ctypes.c_float), ("pass_ms", ctypes.c_float),
         ("keybuild_ms", ctypes.c_float), ("rerank_ms", ctypes.c_float), ("emit_ms", ctypes.c_float),
         ("h2d_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float),
+        ("gen_passes", ctypes.c_uint32), ("gen_pass_ms", ctypes.c_float), ("gen_elements", ctypes.c_uint64),
+        ("host_syncs", ctypes.c_uint32), ("reserved_", ctypes.c_uint32),
     ]
 
     def as_dict(self):

@@ -12,10 +12,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/dark_bwt.h"
@@ -43,7 +47,7 @@ constexpr int kMaxCounters = 4096;
 constexpr u32 kMaxManyBlocks = DARK_BWT_MAX_MANY_BLOCKS;
 constexpr int kMaxEvents = 16 + 10 * DARK_BWT_MAX_ROUNDS;
 
-enum Phase { PH_INIT = 0, PH_SORT, PH_PASS, PH_KEYBUILD, PH_RERANK, PH_EMIT, PH_COUNT };
+enum Phase { PH_INIT = 0, PH_SORT, PH_PASS, PH_GENPASS, PH_KEYBUILD, PH_RERANK, PH_EMIT, PH_COUNT };
 
 struct Mailbox {  // pinned host memory the device results are copied into
     u32 sigma;
@@ -76,8 +80,84 @@ inline int bit_length(u64 x) {
 
 }  // namespace
 
+// Test and tuning knobs, resolved ONCE at dark_bwt_create from the environment (never on the hot path).  The test knobs
+// force code paths that the block size or content would otherwise choose; none of them changes a result, and each has
+// a parity test (tests/test_gpu_parity.py).  The tuning knobs can skip work (garbage output) or select kernels without
+// a forward-progress guarantee, so they exist only in builds with -DDARK_BWT_TUNING (tools/, never shipped).
+struct Knobs {
+    int pass_impl = 1;              // DARK_BWT_PASS_IMPL: 1 = onesweep_tma.cuh, 0 = the round-1 kernel k_onesweep_pass
+    bool force_u64_status = false;  // DARK_BWT_FORCE_U64_STATUS=1
+    bool fused_init = true;         // DARK_BWT_FUSED_INIT=0 materialises the round-0 keys
+    bool gram_hist = true;          // DARK_BWT_GRAM_HIST=0 counts digits key by key
+    bool check_hist = false;        // DARK_BWT_CHECK_HIST=1 counts both ways and compares
+    bool inline_emit = true;        // DARK_BWT_INLINE_EMIT=0
+    bool sparse_rerank = true;      // DARK_BWT_SPARSE_RERANK=0
+    int text_div = 8;               // DARK_BWT_TEXT_BUILD=<k>: text-order key build while m > n/k (0 = never, no isa[] tag)
+    bool pairs = true;              // DARK_BWT_PAIRS=0
+    bool rank_search = true;        // DARK_BWT_RANK_SEARCH=0
+    int bucketed = -1;              // DARK_BWT_BUCKETED=0/1 (-1: by block size)
+    int host_threads = 8;           // DARK_BWT_HOST_THREADS=<t>: staging lanes per direction for pageable host buffers (0: let the driver stage)
+    int sort_variant = -1;          // DARK_BWT_SORT_VARIANT=<i>: run the round-1 kernel with tiling i
+    int emit_window_mb = 64;        // DARK_BWT_EMIT_WINDOW_MB: text window of the emission
+    int ibwt_stride = 48;           // DARK_BWT_IBWT_STRIDE: splitter stride of the inverse BWT
+    bool ibwt_two_walks = false;    // DARK_BWT_IBWT_TWO_WALKS=1
+    // tuning builds only (-DDARK_BWT_TUNING)
+    bool tile_by_blockidx = false;  // DARK_BWT_TILE_BY_BLOCKIDX=1: tiles by blockIdx (no forward-progress guarantee)
+    unsigned knockout = 0;          // DARK_BWT_PASS_KNOCKOUT=<mask>: skip phases of k_onesweep_pass (garbage output)
+    int pass_prefetch = -1;         // DARK_BWT_PASS_PREFETCH=<tiles>
+    int rerank_prefetch = -1;       // DARK_BWT_RERANK_PREFETCH=<tiles>
+    bool group_stats = false;       // DARK_BWT_GROUP_STATS=1
+
+    void read_env() {
+        auto geti = [](const char* name, int dflt) {
+            const char* e = getenv(name);
+            return e ? atoi(e) : dflt;
+        };
+        pass_impl = geti("DARK_BWT_PASS_IMPL", pass_impl);
+        force_u64_status = geti("DARK_BWT_FORCE_U64_STATUS", 0) != 0;
+        fused_init = geti("DARK_BWT_FUSED_INIT", 1) != 0;
+        gram_hist = geti("DARK_BWT_GRAM_HIST", 1) != 0;
+        check_hist = geti("DARK_BWT_CHECK_HIST", 0) != 0;
+        inline_emit = geti("DARK_BWT_INLINE_EMIT", 1) != 0;
+        sparse_rerank = geti("DARK_BWT_SPARSE_RERANK", 1) != 0;
+        text_div = geti("DARK_BWT_TEXT_BUILD", text_div);
+        pairs = geti("DARK_BWT_PAIRS", 1) != 0;
+        rank_search = geti("DARK_BWT_RANK_SEARCH", 1) != 0;
+        bucketed = geti("DARK_BWT_BUCKETED", -1);
+        host_threads = std::min(std::max(geti("DARK_BWT_HOST_THREADS", host_threads), 0), 8);
+        sort_variant = geti("DARK_BWT_SORT_VARIANT", -1);
+        emit_window_mb = std::max(1, geti("DARK_BWT_EMIT_WINDOW_MB", 64));
+        ibwt_stride = std::max(2, geti("DARK_BWT_IBWT_STRIDE", 48));
+        ibwt_two_walks = geti("DARK_BWT_IBWT_TWO_WALKS", 0) != 0;
+#ifdef DARK_BWT_TUNING
+        tile_by_blockidx = geti("DARK_BWT_TILE_BY_BLOCKIDX", 0) != 0;
+        knockout = (unsigned)geti("DARK_BWT_PASS_KNOCKOUT", 0);
+        pass_prefetch = geti("DARK_BWT_PASS_PREFETCH", -1);
+        rerank_prefetch = geti("DARK_BWT_RERANK_PREFETCH", -1);
+        group_stats = geti("DARK_BWT_GROUP_STATS", 0) != 0;
+#endif
+    }
+};
+
+// Pinned staging for PAGEABLE host buffers (the reference hands over a plain Vec<u8>, src/main.rs:95, and collects into a
+// fresh Vec, src/block/dc.rs:47-48).  A cudaMemcpy from pageable memory is staged by the driver through one small
+// bounce buffer on the calling thread (a few GB/s); here `lanes` host threads each own one pinned chunk and a stream:
+// a thread copies a chunk of the caller's buffer into its pinned chunk and sends it on (or receives a chunk and copies
+// it out), so the DMA of one lane overlaps the memcpy of the others.  One set for each direction; allocated on the
+// first pageable call of the context (pinning 64 MB costs tens of milliseconds, contexts that only ever see pinned or
+// device buffers should not pay it).
+struct HostStage {
+    static constexpr size_t kChunk = 8u << 20;
+    static constexpr int kMaxLanes = 8;
+    int lanes = 0;
+    u8* pinned = nullptr;
+    cudaStream_t streams[kMaxLanes] = {nullptr};
+};
+
 struct dark_bwt_ctx {
     int device = 0;
+    Knobs knobs;
+    HostStage stage_in, stage_out;
     int num_sms = 148;
     u64 capacity = 0;
     u32 flags = 0;
@@ -128,6 +208,7 @@ struct dark_bwt_ctx {
     int next_counter = 0;
     u32 tag = 0;  // bit carried by isa[] entries of active suffixes during forward_device (0: not used)
     u32 launches = 0;
+    u32 syncs = 0;
     char err[320] = {0};
 
     int fail_cuda(cudaError_t e, const char* what, int line) {
@@ -152,6 +233,12 @@ struct dark_bwt_ctx {
     } while (0)
 
 namespace {
+
+// every host round trip of a forward call goes through here (dark_bwt_stats.host_syncs)
+inline cudaError_t sync_counted(dark_bwt_ctx* ctx) {
+    ctx->syncs += 1;
+    return cudaStreamSynchronize(ctx->stream);
+}
 
 int span_begin(dark_bwt_ctx* ctx, int phase) {
     if (ctx->n_events + 2 > kMaxEvents - 4) return -1;  // the last events are reserved for the entry points
@@ -187,15 +274,13 @@ int launch_pass_kernel(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* k
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
     auto kern = k_onesweep_pass<THREADS, ITEMS, MINBLOCKS, ILP, StatusT, ALIGNED, GEN>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));  // per device
-    static const bool by_block_index = getenv("DARK_BWT_TILE_BY_BLOCKIDX") != nullptr;
-    const char* ke = getenv("DARK_BWT_PASS_KNOCKOUT");  // measurement only: skip phases (1 look-back, 2 ranking, 4 stores)
-    const u32 knock = ke ? (u32)atoi(ke) : 0u;
+    const bool by_block_index = ctx->knobs.tile_by_blockidx;
+    const u32 knock = ctx->knobs.knockout;  // tuning builds only: skip phases (1 look-back, 2 ranking, 4 stores)
     // persistent grid: as many CTAs as stay resident (SMs x MINBLOCKS), each claiming tiles until none are left
     const u32 grid = by_block_index ? tiles : std::min<u32>(tiles, (u32)ctx->num_sms * MINBLOCKS);
     // L2 prefetch distance in tiles: two thirds of a wave of claims (the persistent grid; 148..444 measured alike, beyond
     // one wave the gain fades) unless DARK_BWT_PASS_PREFETCH says otherwise (0 = off)
-    static const char* ppe = getenv("DARK_BWT_PASS_PREFETCH");
-    const u32 prefetch_ahead = by_block_index ? 0u : (ppe ? (u32)atoi(ppe) : std::max(1u, grid * 2 / 3));
+    const u32 prefetch_ahead = by_block_index ? 0u : (ctx->knobs.pass_prefetch >= 0 ? (u32)ctx->knobs.pass_prefetch : std::max(1u, grid * 2 / 3));
     kern<<<grid, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base, (StatusT*)ctx->sort_status,
                                                         by_block_index ? nullptr : counter, ctx->pass_trace, prev_text, n_text, knock, gen,
                                                         prefetch_ahead);
@@ -259,6 +344,9 @@ int launch_pass_tma(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout
     return 0;
 }
 
+#ifndef DARK_PASS_ILP
+#define DARK_PASS_ILP 2
+#endif
 constexpr int kDefaultSortVariant = 1;  // 256 threads x 16 items, 3 CTAs/SM: best of the sweeps in profiles/r1_sort_variants_*.log
 
 // One onesweep pass over m pairs: buffers[cur] -> buffers[cur^1].
@@ -272,17 +360,16 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
     }
     // 32-bit status words hold prefixes below 2^30; larger sorts (2 GiB blocks) use 64-bit words.
     // DARK_BWT_FORCE_U64_STATUS=1 exercises the wide path on small inputs (tests).
-    const bool wide = !(m < (1u << 30)) || getenv("DARK_BWT_FORCE_U64_STATUS") != nullptr;
-    const char* ev = getenv("DARK_BWT_SORT_VARIANT");
-    const int variant = ev ? atoi(ev) : kDefaultSortVariant;
+    const bool wide = !(m < (1u << 30)) || ctx->knobs.force_u64_status;
+    const bool ev = ctx->knobs.sort_variant >= 0;
+    const int variant = ev ? ctx->knobs.sort_variant : kDefaultSortVariant;
     {
         // default: the TMA-staged pipelined pass; DARK_BWT_PASS_IMPL=0 keeps the round-1 kernel (k_onesweep_pass)
-        const char* pie = getenv("DARK_BWT_PASS_IMPL");
-        const int impl = pie ? atoi(pie) : 1;
-        const bool eligible = (shift & 7) == 0 && ev == nullptr && (gen == nullptr || gen->mode == 0) &&
+        const int impl = ctx->knobs.pass_impl;
+        const bool eligible = (shift & 7) == 0 && !ev && (gen == nullptr || gen->mode == 0) &&
                               (gen != nullptr || (prev_text == nullptr && ((uintptr_t)kin & 15) == 0 && ((uintptr_t)vin & 15) == 0));
         if (impl != 0 && eligible) {
-            return launch_pass_tma<256, 16, 2, 2>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, gen);
+            return launch_pass_tma<256, 16, 2, DARK_PASS_ILP>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, gen);
         }
     }
     if (gen != nullptr) return launch_pass_variant<256, 16, 3, 2>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, n_text, gen);
@@ -317,7 +404,7 @@ int run_sort(dark_bwt_ctx* ctx, u64* const keys[2], u32* const vals[2], int cur,
     // 256 MB block transfers of the pipelined batch entry (measured: +5 ms per block).
     k_scan_hist<<<num_passes, kRadix, 0, ctx->stream>>>(ctx->hist, m, ctx->mail_dev->trivial, ctx->mail_dev->collide);
     LAUNCHED();
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_counted(ctx));
     int first = 0;
     if (prune) {
         for (int p = 0; p < num_passes; ++p)
@@ -337,7 +424,7 @@ int run_sort(dark_bwt_ctx* ctx, u64* const keys[2], u32* const vals[2], int cur,
     if (first_pass_out) *first_pass_out = first;
     // pruned by at least one digit: the first pass that runs also drops the BWT byte into the low key byte
     const u8* patch = (first >= 1) ? patch_text : nullptr;
-    const int sp = span_begin(ctx, PH_PASS);
+    int sp = span_begin(ctx, gen ? PH_GENPASS : PH_PASS);
     for (int p = first; p < num_passes; ++p) {
         if (ctx->mail->trivial[p]) continue;  // every key has the same digit: the pass is the identity
         if (int rc = launch_pass(ctx, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], m, begin_bit + p * kRadixBits,
@@ -346,6 +433,12 @@ int run_sort(dark_bwt_ctx* ctx, u64* const keys[2], u32* const vals[2], int cur,
         if (gen) {  // only the first pass that runs builds its input; the later ones read what it wrote
             if (gen_used_out) *gen_used_out = true;
             gen = nullptr;
+            if (st) {
+                st->gen_passes += 1;
+                st->gen_elements += m;
+            }
+            span_end(ctx, sp);  // the key-generating launch is timed on its own (13 B per suffix, not 24)
+            sp = span_begin(ctx, PH_PASS);
         }
         if (patch) {
             if (patched_out) *patched_out = true;
@@ -378,8 +471,7 @@ int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32
     if (int rc = next_counter(ctx, &counter)) return rc;
     CK(cudaMemsetAsync(ctx->scan_words, 0, sizeof(u64) * kScanWordsPerTile * tiles, ctx->stream));
     ScanTileState ts{ctx->scan_words};
-    static const char* pfe = getenv("DARK_BWT_RERANK_PREFETCH");
-    const u32 prefetch_ahead = pfe ? (u32)atoi(pfe) : 2u * (u32)ctx->num_sms;  // one wave of CTAs ahead (-2 %)
+    const u32 prefetch_ahead = ctx->knobs.rerank_prefetch >= 0 ? (u32)ctx->knobs.rerank_prefetch : 2u * (u32)ctx->num_sms;  // one wave of CTAs ahead (-2 %)
     auto kern = k_rerank<kScanThreads, kScanItems, ROUND0, PAIRS>;
     constexpr size_t smem = (size_t)kScanTile * 8;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -418,7 +510,7 @@ int region_scatter(dark_bwt_ctx* ctx, const u32* ids, const u32* vals, u32 upper
 }
 
 int fetch_count(dark_bwt_ctx* ctx, u32* out) {
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_counted(ctx));
     *out = ctx->mail->count;
     return 0;
 }
@@ -426,11 +518,11 @@ int fetch_count(dark_bwt_ctx* ctx, u32* out) {
 int emit(dark_bwt_ctx* ctx, const u8* d_text, u32 n, const u32* d_sa, u8* d_bwt) {
     const u32 blocks = (u32)ceil_div(ceil_div(n, 4), 256);
     const bool aligned = (((uintptr_t)d_bwt) & 3) == 0;
+    const int sa16 = (((uintptr_t)d_sa) & 15) == 0 ? 1 : 0;  // else the kernels read the SA word by word
     // text window kept L2-resident per launch (126 MB L2); DARK_BWT_EMIT_WINDOW_MB overrides for sweeps
-    const char* ev = getenv("DARK_BWT_EMIT_WINDOW_MB");
-    const u64 window = (u64)(ev ? std::max(1, atoi(ev)) : 64) << 20;
+    const u64 window = (u64)ctx->knobs.emit_window_mb << 20;
     if (!aligned || n <= window + window / 2) {  // small block or odd output pointer: one plain gather launch
-        k_emit_bwt<256><<<blocks, 256, 0, ctx->stream>>>(d_text, n, d_sa, d_bwt, &ctx->mail_dev->origin, aligned ? 1 : 0);
+        k_emit_bwt<256><<<blocks, 256, 0, ctx->stream>>>(d_text, n, d_sa, d_bwt, &ctx->mail_dev->origin, aligned ? 1 : 0, sa16);
         LAUNCHED();
         return 0;
     }
@@ -441,9 +533,9 @@ int emit(dark_bwt_ctx* ctx, const u8* d_text, u32 n, const u32* d_sa, u8* d_bwt)
     for (u32 w = 0; w < nwin; ++w) {
         const u32 lo = (u32)(w * step), hi = (u32)std::min<u64>((u64)n, (w + 1) * step);
         if (w == 0)
-            k_emit_bwt_window<256, true><<<blocks, 256, 0, ctx->stream>>>(d_text, n, d_sa, d_bwt, &ctx->mail_dev->origin, lo, hi);
+            k_emit_bwt_window<256, true><<<blocks, 256, 0, ctx->stream>>>(d_text, n, d_sa, d_bwt, &ctx->mail_dev->origin, lo, hi, sa16);
         else
-            k_emit_bwt_window<256, false><<<blocks, 256, 0, ctx->stream>>>(d_text, n, d_sa, d_bwt, &ctx->mail_dev->origin, lo, hi);
+            k_emit_bwt_window<256, false><<<blocks, 256, 0, ctx->stream>>>(d_text, n, d_sa, d_bwt, &ctx->mail_dev->origin, lo, hi, sa16);
         LAUNCHED();
     }
     return 0;
@@ -462,12 +554,14 @@ void finish_stats(dark_bwt_ctx* ctx, dark_bwt_stats* st, int e_first, int e_last
             case PH_INIT: st->init_ms += t; break;
             case PH_SORT: st->sort_ms += t; break;
             case PH_PASS: st->pass_ms += t; break;
+            case PH_GENPASS: st->pass_ms += t; st->gen_pass_ms += t; break;
             case PH_KEYBUILD: st->keybuild_ms += t; break;
             case PH_RERANK: st->rerank_ms += t; break;
             case PH_EMIT: st->emit_ms += t; break;
         }
     }
     st->kernel_launches = ctx->launches;
+    st->host_syncs = ctx->syncs;
 }
 
 // The whole forward transform on device buffers.  d_sa_user nullable.
@@ -480,6 +574,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     ctx->spans.clear();
     ctx->next_counter = 0;
     ctx->launches = 0;
+    ctx->syncs = 0;
     if (st) {
         const float h2d = st->h2d_ms;
         memset(st, 0, sizeof(*st));
@@ -505,7 +600,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         k_build_lut<<<1, 256, 0, ctx->stream>>>(ctx->present, ctx->lut, &ctx->mail_dev->sigma, no_pack);
         LAUNCHED();
     }
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_counted(ctx));
     const u32 sigma = ctx->mail->sigma;
     if (sigma < 1 || sigma > 256) return ctx->fail_internal("alphabet scan returned an impossible sigma");
     const int s_bits = no_pack ? 8 : std::max(1, bit_length(sigma - 1));
@@ -520,11 +615,10 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     // ---- round 0: keys of K symbols, ids descending
     // Fused initial keys (s in {1,2,4,8}): the key builder only counts digits; the first radix pass that runs
     // rebuilds the keys from the text (radix_sort.cuh, GEN).  DARK_BWT_FUSED_INIT=0 materialises them instead.
-    const char* fev = getenv("DARK_BWT_FUSED_INIT");
+    const Knobs& kn = ctx->knobs;
     const bool packed_s = s_bits == 1 || s_bits == 2 || s_bits == 4 || s_bits == 8;
-    const bool fuse_init = packed_s && (fev ? atoi(fev) != 0 : true) && getenv("DARK_BWT_SORT_VARIANT") == nullptr;
-    const char* gev = getenv("DARK_BWT_GRAM_HIST");
-    const bool gram_hist = packed_s && (gev ? atoi(gev) != 0 : true);  // histograms from the text's q-grams (suffix_kernels.cuh)
+    const bool fuse_init = packed_s && kn.fused_init && kn.sort_variant < 0;
+    const bool gram_hist = packed_s && kn.gram_hist;  // histograms from the text's q-grams (suffix_kernels.cuh)
     const int lg_s = s_bits == 1 ? 0 : s_bits == 2 ? 1 : s_bits == 4 ? 2 : 3;
     auto init_keys = [&](bool write, bool hist) -> int {
         const u32 blocks = (u32)std::min<u64>(ceil_div(n, kInitThreads * kInitItems), (u64)ctx->num_sms * 8);
@@ -566,16 +660,16 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         LAUNCHED();
         k_gram_expand<<<1, kRadix, 0, ctx->stream>>>(d_text, n, ctx->lut, lg_s, gram, ctx->hist);
         LAUNCHED();
-        if (getenv("DARK_BWT_CHECK_HIST")) {  // test hook: compare with the histogram counted key by key
+        if (kn.check_hist) {  // test hook: compare with the histogram counted key by key
             std::vector<u32> a(kMaxPasses * kRadix), b(kMaxPasses * kRadix);
             CK(cudaMemcpyAsync(a.data(), ctx->hist, a.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaMemsetAsync(ctx->hist, 0, sizeof(u32) * kMaxPasses * kRadix, ctx->stream));
             if (int rc = init_keys(false, true)) return rc;
             CK(cudaMemcpyAsync(b.data(), ctx->hist, b.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(sync_counted(ctx));
             if (a != b) return ctx->fail_internal("q-gram histogram differs from the per-key histogram");
             CK(cudaMemcpyAsync(ctx->hist, a.data(), a.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(sync_counted(ctx));
         }
         if (!fuse_init)
             if (int rc = init_keys(true, false)) return rc;
@@ -589,8 +683,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     sp = span_begin(ctx, PH_SORT);
     // Inline emission: when the initial sort is pruned by >= 1 digit the BWT byte of each suffix travels in
     // the (unsorted) low key byte and is emitted as the suffix settles; no gather pass at the end.
-    const char* iev = getenv("DARK_BWT_INLINE_EMIT");
-    const bool want_inline = iev ? atoi(iev) != 0 : true;
+    const bool want_inline = kn.inline_emit;
     bool emit_inline = false;
     KeyGen gen;
     gen.text = d_text;
@@ -627,8 +720,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     bool sparse_done = false;
     // Pruned initial sort with inline emission (high-entropy block: almost everything settles): the chain-free
     // sparse re-rank (suffix_kernels.cuh).  DARK_BWT_SPARSE_RERANK=0 keeps the scan-based kernel.
-    static const char* spe = getenv("DARK_BWT_SPARSE_RERANK");
-    if (emit_inline && first_pass >= 1 && (spe ? atoi(spe) != 0 : true)) {
+    if (emit_inline && first_pass >= 1 && kn.sparse_rerank) {
         u32 *total = nullptr, *ovf = nullptr;
         if (int rc = next_counter(ctx, &total)) return rc;
         if (int rc = next_counter(ctx, &ovf)) return rc;
@@ -658,7 +750,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
             LAUNCHED();
             k_copy_u32<<<1, 1, 0, ctx->stream>>>(ovf, &ctx->mail_dev->flag);
             LAUNCHED();
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(sync_counted(ctx));
             if (ctx->mail->flag == 0) {
                 sparse_done = true;
                 m = survivors;
@@ -678,18 +770,14 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     int selective_rounds = 0;
     // isa[] entries of active suffixes carry bit 31 (blocks up to 2^31 bytes): the text-order key builder finds
     // them by it.  DARK_BWT_TEXT_BUILD=0 switches tag and builder off; =<k> uses the builder while m > n/k.
-    const char* tev = getenv("DARK_BWT_TEXT_BUILD");
-    const int text_div = tev ? atoi(tev) : 8;
+    const int text_div = kn.text_div;
     const u32 tag = (text_div > 0 && (u64)n <= (1ull << 31)) ? 0x80000000u : 0u;
     ctx->tag = tag;
-    const char* pev = getenv("DARK_BWT_PAIRS");
-    const bool use_pairs = pev ? atoi(pev) != 0 : true;
+    const bool use_pairs = kn.pairs;
     bool pairs_mode = false;
-    const char* sev = getenv("DARK_BWT_RANK_SEARCH");
-    const bool use_search = sev ? atoi(sev) != 0 : true;
+    const bool use_search = kn.rank_search;
     // Scatters of more than n/16 ranks into an isa[] that outgrows L2 go through the bucketed path.
-    const char* bev = getenv("DARK_BWT_BUCKETED");
-    const bool bucketed = bev ? atoi(bev) != 0 : ((u64)n * 4 > (96ull << 20));
+    const bool bucketed = kn.bucketed >= 0 ? kn.bucketed != 0 : ((u64)n * 4 > (96ull << 20));
     const int bshift = std::max(0, bit_length((u64)n - 1) - 8);
     if (m > 0) {
         sp = span_begin(ctx, PH_RERANK);
@@ -732,7 +820,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
             if (int rc = next_counter(ctx, &seen)) return rc;
             k_pairs_detect<<<(u32)ceil_div(m, 256), 256, 0, ctx->stream>>>(ctx->ranks, m, seen, &ctx->mail_dev->flag);
             LAUNCHED();
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(sync_counted(ctx));
             if (ctx->mail->flag == 0) {
                 pairs_mode = true;
             }
@@ -765,13 +853,13 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
             ++round;
             continue;
         }
-        if (getenv("DARK_BWT_GROUP_STATS")) {  // debug: group-size statistics of the active list
+        if (kn.group_stats) {  // debug: group-size statistics of the active list
             CK(cudaMemsetAsync(ctx->bucket_hist, 0, 8, ctx->stream));
             k_group_stats<<<(u32)ceil_div(m, 256), 256, 0, ctx->stream>>>(ctx->ranks, m, ctx->bucket_hist);
             LAUNCHED();
             u32 gs[2] = {0, 0};
             CK(cudaMemcpyAsync(gs, ctx->bucket_hist, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(sync_counted(ctx));
             fprintf(stderr, "[dark_bwt] round %d: h=%llu active=%u groups=%u max_group=%u%s\n", round, (unsigned long long)h, m, gs[1],
                     gs[0], gs[0] >= 4096 ? "+" : "");
         }
@@ -862,7 +950,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     span_end(ctx, sp);
     const int e_last = ctx->n_events++;
     CK(cudaEventRecord(ctx->events[e_last], ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_counted(ctx));
     *origin_out = ctx->mail->origin;
     finish_stats(ctx, st, e_first, e_last);
     return DARK_BWT_OK;
@@ -1022,19 +1110,17 @@ int inverse_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, u64 origin64, u8
     }
     const u32* psi1 = ctx->ids[cur];
     // step 2: sublists between splitters
-    const char* se = getenv("DARK_BWT_IBWT_STRIDE");  // rows between splitters (sweeps only)
-    const u32 stride = se ? (u32)std::max(2, atoi(se)) : 48u;  // swept 24..128 with the single walk: 48 (profiles/r1_final.md)
+    const u32 stride = (u32)ctx->knobs.ibwt_stride;  // rows between splitters; swept 24..128 with the single walk: 48 (profiles/r1_final.md)
     const u32 head = origin + 1;
     const u32 regular = (u32)ceil_div((u64)n + 1, stride);
     const u32 nodes = regular + 1;
     u32* dist[2] = {ctx->ranks, ctx->sa};
     u32* next[2] = {ctx->isa, ctx->ids[cur ^ 1]};
     // one walk: count the sublists and stash their symbols (DARK_BWT_IBWT_TWO_WALKS=1: count, then a second walk writes)
-    static const char* twe = getenv("DARK_BWT_IBWT_TWO_WALKS");
     u32* len_keep = ctx->ranks_alt;
     u32* stash = (u32*)ctx->keys[cur ^ 1];  // the sort's other key buffer (8 n + 1024 bytes) is free: nodes * 384 <= 6 n + 768
     const u32 cap = (u32)std::min<u64>(kIbwtStashCap, (((u64)n * 8 + 1024) / nodes) & ~3ull);  // smaller strides: smaller chunks
-    const bool two_walks = (twe && atoi(twe) != 0) || cap < 8;
+    const bool two_walks = ctx->knobs.ibwt_two_walks || cap < 8;
     // k_ibwt_walk needs the symbol bases (exclusive digit counts of pass 0, left in ctx->hist by run_sort)
     if (two_walks)
         k_ibwt_walk<0><<<(u32)ceil_div(nodes, 128), 128, 0, ctx->stream>>>(psi1, n, head, stride, regular, dist[0], next[0], nullptr, nullptr,
@@ -1074,6 +1160,97 @@ int inverse_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, u64 origin64, u8
     CK(cudaStreamSynchronize(ctx->stream));
     if (ms_out) cudaEventElapsedTime(ms_out, ea, eb);
     return DARK_BWT_OK;
+}
+
+// ---- pageable host buffers ---------------------------------------------------------------------
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int stage_prepare(dark_bwt_ctx* ctx, HostStage& st) {
+    if (st.lanes > 0) return 0;
+    const int lanes = ctx->knobs.host_threads;
+    if (lanes <= 0) return 1;  // staging switched off
+    if (cudaHostAlloc((void**)&st.pinned, HostStage::kChunk * lanes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        st.pinned = nullptr;
+        return 1;  // no pinned memory to be had: fall back to the driver's own staging
+    }
+    for (int i = 0; i < lanes; ++i)
+        if (cudaStreamCreateWithFlags(&st.streams[i], cudaStreamNonBlocking) != cudaSuccess) return ctx->fail_cuda(cudaGetLastError(), "staging stream", __LINE__);
+    st.lanes = lanes;
+    return 0;
+}
+
+void stage_release(HostStage& st) {
+    for (int i = 0; i < HostStage::kMaxLanes; ++i)
+        if (st.streams[i]) cudaStreamDestroy(st.streams[i]);
+    if (st.pinned) cudaFreeHost(st.pinned);
+    st = HostStage();
+}
+
+// Copies `bytes` between a pageable host buffer and device memory through the lanes of `st`; returns when done.
+// The caller has made sure that the device side is ready (H2D: the buffer is free; D2H: the data is complete).
+int staged_copy(dark_bwt_ctx* ctx, HostStage& st, void* dev, void* host, size_t bytes, bool to_device) {
+    const size_t nchunks = (bytes + HostStage::kChunk - 1) / HostStage::kChunk;
+    const int lanes = (int)std::min<size_t>((size_t)st.lanes, nchunks);
+    std::atomic<size_t> next(0);
+    std::atomic<int> failed(0);
+    auto work = [&](int lane) {
+        if (cudaSetDevice(ctx->device) != cudaSuccess) {
+            failed = 1;
+            return;
+        }
+        u8* slot = st.pinned + (size_t)lane * HostStage::kChunk;
+        cudaStream_t sm = st.streams[lane];
+        for (;;) {
+            const size_t c = next.fetch_add(1);
+            if (c >= nchunks || failed.load()) break;
+            const size_t off = c * HostStage::kChunk, len = std::min(HostStage::kChunk, bytes - off);
+            if (to_device) {
+                memcpy(slot, (const u8*)host + off, len);
+                if (cudaMemcpyAsync((u8*)dev + off, slot, len, cudaMemcpyHostToDevice, sm) != cudaSuccess || cudaStreamSynchronize(sm) != cudaSuccess) failed = 1;
+            } else {
+                if (cudaMemcpyAsync(slot, (const u8*)dev + off, len, cudaMemcpyDeviceToHost, sm) != cudaSuccess || cudaStreamSynchronize(sm) != cudaSuccess) failed = 1;
+                else memcpy((u8*)host + off, slot, len);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int i = 1; i < lanes; ++i) pool.emplace_back(work, i);
+    work(0);
+    for (auto& t : pool) t.join();
+    if (failed.load()) return ctx->fail_cuda(cudaGetLastError(), "staged host copy", __LINE__);
+    return 0;
+}
+
+constexpr size_t kStageMinBytes = 1u << 20;  // smaller copies go straight to cudaMemcpyAsync
+
+// host -> device on `stream` semantics: returns after the copy has completed
+int copy_in_blocking(dark_bwt_ctx* ctx, u8* dev, const u8* host, size_t bytes, cudaStream_t stream) {
+    if (bytes >= kStageMinBytes && is_pageable(host)) {
+        const int rc = stage_prepare(ctx, ctx->stage_in);
+        if (rc > 1) return rc;
+        if (rc == 0) return staged_copy(ctx, ctx->stage_in, dev, (void*)host, bytes, true);
+    }
+    CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+}
+int copy_out_blocking(dark_bwt_ctx* ctx, void* host, const void* dev, size_t bytes, cudaStream_t stream) {
+    if (bytes >= kStageMinBytes && is_pageable(host)) {
+        const int rc = stage_prepare(ctx, ctx->stage_out);
+        if (rc > 1) return rc;
+        if (rc == 0) return staged_copy(ctx, ctx->stage_out, (void*)dev, host, bytes, false);
+    }
+    CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
 }
 
 }  // namespace
@@ -1122,6 +1299,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     }
     ctx->capacity = max_n;
     ctx->flags = flags;
+    ctx->knobs.read_env();
 
     const size_t N = (size_t)max_n;
     const size_t sort_tiles = ceil_div(N, kSortTile);
@@ -1224,6 +1402,8 @@ void dark_bwt_destroy(dark_bwt_ctx* ctx) {
         if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
         if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
     }
+    stage_release(ctx->stage_in);
+    stage_release(ctx->stage_out);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1248,22 +1428,20 @@ int dark_bwt_forward(dark_bwt_ctx* ctx, const uint8_t* text, uint64_t n, uint8_t
     if (ctx->flags & DARK_BWT_F_DEVICE_ONLY) return DARK_BWT_E_INVALID_ARG;
     if (n < 2 || n > ctx->capacity || n > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;
     CK(cudaSetDevice(ctx->device));
-    cudaEvent_t a = ctx->events[kMaxEvents - 1], b = ctx->events[kMaxEvents - 2];
-    CK(cudaEventRecord(a, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_text, text, n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaEventRecord(b, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    float h2d = 0.f;
-    cudaEventElapsedTime(&h2d, a, b);
+    // pinned (or registered) buffers are copied directly, pageable ones through the context's pinned staging lanes
+    typedef std::chrono::steady_clock Clock;
+    auto ms_since = [](Clock::time_point t0) { return std::chrono::duration<float, std::milli>(Clock::now() - t0).count(); };
+    Clock::time_point t0 = Clock::now();
+    if (int rc = copy_in_blocking(ctx, ctx->d_text, text, n, ctx->stream)) return rc;
+    const float h2d = ms_since(t0);
     if (stats) stats->h2d_ms = h2d;
     int rc = forward_device(ctx, ctx->d_text, n, ctx->d_bwt, origin_out, nullptr, stats);
     if (rc) return rc;
-    CK(cudaEventRecord(a, ctx->stream));
-    CK(cudaMemcpyAsync(bwt_out, ctx->d_bwt, n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (sa_out) CK(cudaMemcpyAsync(sa_out, ctx->sa, n * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaEventRecord(b, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (stats) cudaEventElapsedTime(&stats->d2h_ms, a, b);
+    t0 = Clock::now();
+    if (int rc2 = copy_out_blocking(ctx, bwt_out, ctx->d_bwt, n, ctx->stream)) return rc2;
+    if (sa_out)
+        if (int rc2 = copy_out_blocking(ctx, sa_out, ctx->sa, n * sizeof(u32), ctx->stream)) return rc2;
+    if (stats) stats->d2h_ms = ms_since(t0);
     return DARK_BWT_OK;
 }
 
@@ -1281,34 +1459,77 @@ int dark_bwt_forward_batch(dark_bwt_ctx* ctx, const uint8_t* const* texts, const
     u8* d_text[2] = {ctx->d_text, ctx->d_text2};
     u8* d_bwt[2] = {ctx->d_bwt, ctx->d_bwt2};
     bool comp_recorded[2] = {false, false}, out_recorded[2] = {false, false};
-    // prologue: block 0 in
-    CK(cudaMemcpyAsync(d_text[0], texts[0], ns[0], cudaMemcpyHostToDevice, ctx->copy_in));
-    CK(cudaEventRecord(ctx->ev_in[0], ctx->copy_in));
+    // Pinned host buffers ride on the two copy streams; pageable ones (>= 1 MiB) are moved by the staging lanes in a
+    // helper thread, so that either way block k+1 comes in and block k-1 goes out while block k is transformed.
+    std::future<int> fin[2], fout;
+    auto staged_in = [&](uint64_t k) { return ns[k] >= kStageMinBytes && is_pageable(texts[k]) && stage_prepare(ctx, ctx->stage_in) == 0; };
+    auto staged_out = [&](uint64_t k) { return ns[k] >= kStageMinBytes && is_pageable(bwt_outs[k]) && stage_prepare(ctx, ctx->stage_out) == 0; };
+    auto start_in = [&](uint64_t k, int buf) -> int {  // the transform that read d_text[buf] has returned (forward_device is synchronous)
+        if (staged_in(k)) {
+            u8* dst = d_text[buf];
+            const u8* src = texts[k];
+            const size_t bytes = ns[k];
+            fin[buf] = std::async(std::launch::async, [ctx, dst, src, bytes] { return staged_copy(ctx, ctx->stage_in, dst, (void*)src, bytes, true); });
+            return 0;
+        }
+        if (comp_recorded[buf]) CK(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[buf], 0));
+        CK(cudaMemcpyAsync(d_text[buf], texts[k], ns[k], cudaMemcpyHostToDevice, ctx->copy_in));
+        CK(cudaEventRecord(ctx->ev_in[buf], ctx->copy_in));
+        return 0;
+    };
+    auto drain = [&]() {  // never leave a helper thread behind
+        int rc = 0;
+        for (int i = 0; i < 2; ++i)
+            if (fin[i].valid()) rc |= fin[i].get();
+        if (fout.valid()) rc |= fout.get();
+        return rc;
+    };
+    if (int rc = start_in(0, 0)) return rc;
     for (uint64_t k = 0; k < count; ++k) {
         const int b = (int)(k & 1), nb = b ^ 1;
-        if (k + 1 < count) {  // next block in, once the transform that read that buffer is done
-            if (comp_recorded[nb]) CK(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[nb], 0));
-            CK(cudaMemcpyAsync(d_text[nb], texts[k + 1], ns[k + 1], cudaMemcpyHostToDevice, ctx->copy_in));
-            CK(cudaEventRecord(ctx->ev_in[nb], ctx->copy_in));
+        if (fin[b].valid()) {
+            if (int rc = fin[b].get()) { drain(); return rc; }
+        } else {
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
         }
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+        if (k + 1 < count)
+            if (int rc = start_in(k + 1, nb)) { drain(); return rc; }
+        // (a staged copy-out of block k-1 may still be reading the OTHER BWT buffer; this one was drained before it began)
         if (out_recorded[b]) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));  // BWT buffer b drained
         u32* sa_user = (sa_outs && sa_outs[k]) ? sa_outs[k] : nullptr;
         dark_bwt_stats* st = stats ? stats + k : nullptr;
         if (st) st->h2d_ms = 0.f;
         int rc = forward_device(ctx, d_text[b], ns[k], d_bwt[b], origins_out + k, nullptr, st);
-        if (rc) return rc;
+        if (rc) { drain(); return rc; }
         CK(cudaEventRecord(ctx->ev_comp[b], ctx->stream));
         comp_recorded[b] = true;
-        CK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[b], 0));
-        CK(cudaMemcpyAsync(bwt_outs[k], d_bwt[b], ns[k], cudaMemcpyDeviceToHost, ctx->copy_out));
-        if (sa_user) {  // the single SA buffer is reused by the next block: drain it before going on
-            CK(cudaMemcpyAsync(sa_user, ctx->sa, ns[k] * sizeof(u32), cudaMemcpyDeviceToHost, ctx->copy_out));
-            CK(cudaStreamSynchronize(ctx->copy_out));
+        if (fout.valid())
+            if (int rc2 = fout.get()) { drain(); return rc2; }  // one staged copy-out at a time (they share the lanes)
+        if (staged_out(k)) {
+            u8* dst = bwt_outs[k];
+            const u8* src = d_bwt[b];
+            const size_t bytes = ns[k];
+            const u32* sa_src = ctx->sa;
+            fout = std::async(std::launch::async, [ctx, dst, src, bytes, sa_user, sa_src] {
+                int r = staged_copy(ctx, ctx->stage_out, (void*)src, dst, bytes, false);
+                if (r == 0 && sa_user) r = staged_copy(ctx, ctx->stage_out, (void*)sa_src, sa_user, bytes * sizeof(u32), false);
+                return r;
+            });
+            if (sa_user)
+                if (int rc2 = fout.get()) { drain(); return rc2; }  // the single SA buffer is reused by the next block
+            out_recorded[b] = false;
+        } else {
+            CK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[b], 0));
+            CK(cudaMemcpyAsync(bwt_outs[k], d_bwt[b], ns[k], cudaMemcpyDeviceToHost, ctx->copy_out));
+            if (sa_user) {  // the single SA buffer is reused by the next block: drain it before going on
+                CK(cudaMemcpyAsync(sa_user, ctx->sa, ns[k] * sizeof(u32), cudaMemcpyDeviceToHost, ctx->copy_out));
+                CK(cudaStreamSynchronize(ctx->copy_out));
+            }
+            CK(cudaEventRecord(ctx->ev_out[b], ctx->copy_out));
+            out_recorded[b] = true;
         }
-        CK(cudaEventRecord(ctx->ev_out[b], ctx->copy_out));
-        out_recorded[b] = true;
     }
+    if (int rc = drain()) return rc;
     CK(cudaStreamSynchronize(ctx->copy_out));
     CK(cudaStreamSynchronize(ctx->copy_in));
     return DARK_BWT_OK;
@@ -1390,11 +1611,9 @@ int dark_bwt_inverse(dark_bwt_ctx* ctx, const uint8_t* bwt, uint64_t n, uint64_t
     if (n < 1 || n > ctx->capacity || n > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;
     ctx->err[0] = 0;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(ctx->d_bwt, bwt, n, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = copy_in_blocking(ctx, ctx->d_bwt, bwt, n, ctx->stream)) return rc;
     if (int rc = inverse_device(ctx, ctx->d_bwt, n, origin, ctx->d_text, nullptr)) return rc;
-    CK(cudaMemcpyAsync(text_out, ctx->d_text, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return DARK_BWT_OK;
+    return copy_out_blocking(ctx, text_out, ctx->d_text, n, ctx->stream);
 }
 
 int dark_bwt_reuse(dark_bwt_ctx* ctx, uint32_t** words_out, uint64_t* count_out) {
@@ -1469,14 +1688,24 @@ int dark_bwt_verify_sa_device(dark_bwt_ctx* ctx, const uint8_t* d_text, uint64_t
 // written to d_trace ([tiles][8] long long); nullptr switches tracing off.
 int dark_bwt_debug_trace_rerank(dark_bwt_ctx* ctx, long long* d_trace) {
     if (!ctx) return DARK_BWT_E_INVALID_ARG;
+#if defined(DARK_BWT_TUNING) || defined(DARK_TUNE_TRACE)
     ctx->rerank_trace = d_trace;
     return DARK_BWT_OK;
+#else
+    (void)d_trace;
+    return DARK_BWT_E_INVALID_ARG;  // tracing exists in tuning builds only
+#endif
 }
 
 int dark_bwt_debug_trace(dark_bwt_ctx* ctx, long long* d_trace) {
     if (!ctx) return DARK_BWT_E_INVALID_ARG;
+#if defined(DARK_BWT_TUNING) || defined(DARK_TUNE_TRACE)
     ctx->pass_trace = d_trace;
     return DARK_BWT_OK;
+#else
+    (void)d_trace;
+    return DARK_BWT_E_INVALID_ARG;  // tracing exists in tuning builds only
+#endif
 }
 
 int dark_bwt_lcp_profile_device(dark_bwt_ctx* ctx, const uint8_t* d_text, uint64_t n64, const uint32_t* d_sa, uint64_t* m_out,

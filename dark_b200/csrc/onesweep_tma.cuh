@@ -45,6 +45,7 @@ struct PipeSmem {
     u8 lut[256];
 };
 
+static_assert(DARK_SCANNERS >= 1 && 256 % DARK_SCANNERS == 0, "every digit needs a scanner: the scanner count must divide 256");
 constexpr int kScanners = DARK_SCANNERS;  // scanner CTAs per pass: each owns 256 / kScanners digits (tickets 0 .. kScanners-1)
 constexpr int kScannerBatch = 32;      // status rows per scanner batch (three in flight: 3 * 32 zeroed rows follow the last tile)
 constexpr u32 kGenStageBytes = 4288;   // text slice of a 4,096-suffix tile: 4,096 + 64 symbols of look-ahead + alignment slack

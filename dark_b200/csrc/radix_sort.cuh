@@ -245,7 +245,13 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
                                               const KeyGen gen) {
     // knock != 0 (tools/sort_bench.py KNOCKOUT only): phases are skipped to measure what they cost; output is garbage
     // trace != nullptr (tools/pass_trace.py only): thread 0 stamps clock64() at the phase boundaries
+#ifdef DARK_BWT_TUNING
 #define DARK_STAMP(i) do { if (trace && threadIdx.x == 0) trace[(size_t)tile * 12 + (i)] = clock64(); } while (0)
+#define DARK_KNOCK(bit) (knock & (bit))
+#else
+#define DARK_STAMP(i) do { (void)trace; } while (0)
+#define DARK_KNOCK(bit) ((void)knock, false)
+#endif
     typedef OnesweepSmem<THREADS, ITEMS> Smem;
     typedef StatusTraits<StatusT> ST;
     constexpr int TILE = Smem::kTile;
@@ -358,7 +364,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
         // ILP items stay in flight per warp.
         if (k >= ILP) asm volatile("" : "+r"(d) : "r"(rank2[(k - ILP) / 2]));
         u32 peers = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
-        if (knock & 2u) peers = 1u << lane;
+        if (DARK_KNOCK(2u)) peers = 1u << lane;
         else peers = match_digit_bits(peers, d);
         const u32 prev = whist[d];  // every lane reads (padding lanes harmlessly), then the group's lowest lane bumps
         const u32 below = peers & lt;
@@ -424,7 +430,7 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
     // nearest inclusive prefix is 10-25 tiles back: walking them one load at a time cost 34 % of the
     // tile time (profiles/r1_pass_trace_v3.log); 8 predecessors are read per round trip.
     if (tid < kRadix) {
-        if (tile > 0 && !(knock & 1u)) {
+        if (tile > 0 && !DARK_KNOCK(1u)) {
             lb.finish(status, tid);
             st_relaxed(status + (size_t)tile * kRadix + tid, ((StatusT)2 << ST::kShift) | (lb.excl + count));
         }
@@ -440,19 +446,22 @@ __device__ __forceinline__ void onesweep_tile(OnesweepSmem<THREADS, ITEMS>& s, c
         if (FULL || p < nvalid) {
             const u64 kk = s.keys[p];
             const u32 idx = s.global_off[digit(kk)] + p;
-            if (!(knock & 4u)) {
+            if (!DARK_KNOCK(4u)) {
                 keys_out[idx] = kk;
                 vals_out[idx] = s.vals[p];
             }
         }
     }
     DARK_STAMP(7);
+#ifdef DARK_BWT_TUNING
     if (trace && threadIdx.x == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         trace[(size_t)tile * 12 + 10] = (long long)gt;
     }
+#endif
 #undef DARK_STAMP
+#undef DARK_KNOCK
 }
 
 template <int THREADS, int ITEMS, int MINBLOCKS, int ILP, typename StatusT, bool ALIGNED, bool GEN = false>
@@ -476,12 +485,15 @@ k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in
     // tile_counter == nullptr (test knob) falls back to one tile per CTA numbered by blockIdx.x.
     const u32 num_tiles = (u32)(((u64)m + TILE - 1) / TILE);
     for (;;) {
+#ifdef DARK_BWT_TUNING
         const long long t_claim = trace ? clock64() : 0;
+#endif
         if (tile_counter != nullptr && tid == 0) s.tile = atomicAdd(tile_counter, 1u);
         for (int i = tid; i < Smem::kWarps * kRadix; i += THREADS) (&s.warp_hist[0][0])[i] = 0;
         __syncthreads();
         const u32 tile = tile_counter != nullptr ? s.tile : blockIdx.x;
         if (tile >= num_tiles) break;
+#ifdef DARK_BWT_TUNING
         if (trace && tid == 0) {
             trace[(size_t)tile * 12 + 0] = t_claim;
             trace[(size_t)tile * 12 + 1] = clock64();
@@ -492,6 +504,7 @@ k_onesweep_pass(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in
             trace[(size_t)tile * 12 + 8] = (long long)gt;
             trace[(size_t)tile * 12 + 9] = (long long)smid;
         }
+#endif
         const u32 nvalid = (u32)min((u64)TILE, (u64)m - (u64)tile * TILE);
         if (!GEN && prefetch_ahead) {
             // Pull the pairs of the tile this CTA is likely to claim next (one wave of claims ahead) into L2, a

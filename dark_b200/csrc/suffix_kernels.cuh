@@ -1342,11 +1342,11 @@ k_partition_pairs(const u32* __restrict__ ids, const u32* __restrict__ vals, u32
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_emit_bwt(const u8* __restrict__ text, u32 n, const u32* __restrict__ sa, u8* __restrict__ bwt, u64* __restrict__ origin,
-           int bwt_aligned4) {
+           int bwt_aligned4, int sa_aligned16) {
     const u64 j0 = ((u64)blockIdx.x * THREADS + threadIdx.x) * 4;
     if (j0 >= n) return;
     u32 s[4];
-    if (j0 + 4 <= n) {
+    if (j0 + 4 <= n && sa_aligned16) {  // 128-bit SA loads need a 16-byte aligned SA (a caller's d_sa may be a 4-byte aligned slice)
         const uint4 q = *reinterpret_cast<const uint4*>(sa + j0);
         s[0] = q.x; s[1] = q.y; s[2] = q.z; s[3] = q.w;
     } else {
@@ -1388,12 +1388,12 @@ __device__ __forceinline__ u32 ld_u8_keep(const u8* p, u64 pol) {
 template <int THREADS, bool FIRST>
 __global__ void __launch_bounds__(THREADS)
 k_emit_bwt_window(const u8* __restrict__ text, u32 n, const u32* __restrict__ sa, u8* __restrict__ bwt, u64* __restrict__ origin,
-                  u32 win_lo, u32 win_hi) {
+                  u32 win_lo, u32 win_hi, int sa_aligned16) {
     const u64 j0 = ((u64)blockIdx.x * THREADS + threadIdx.x) * 4;
     if (j0 >= n) return;
     const u64 pol = l2_policy_evict_last();
     u32 s[4];
-    if (j0 + 4 <= n) {
+    if (j0 + 4 <= n && sa_aligned16) {
         uint4 q;
         asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(sa + j0));
         s[0] = q.x; s[1] = q.y; s[2] = q.z; s[3] = q.w;

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define DARK_BWT_ABI_VERSION 1
+#define DARK_BWT_ABI_VERSION 2
 
 /* error codes (0 = ok) */
 #define DARK_BWT_OK 0
@@ -89,6 +89,12 @@ typedef struct dark_bwt_stats {
     float emit_ms;            /* BWT gather + origin                                      */
     float h2d_ms;             /* host entry point only                                    */
     float d2h_ms;             /* host entry point only                                    */
+    /* the key-generating first pass (reads 1 B of text and writes 12 B per suffix instead of 12 + 12), part of the figures above */
+    uint32_t gen_passes;      /* key-generating pass launches (0 or 1)                    */
+    float gen_pass_ms;        /* their share of pass_ms                                   */
+    uint64_t gen_elements;    /* their share of sorted_elements                           */
+    uint32_t host_syncs;      /* stream synchronisations this call needed (host round trips) */
+    uint32_t reserved_;
 } dark_bwt_stats;
 
 /* Constructor::new — allocates every device buffer for blocks of up to max_n bytes on

@@ -32,6 +32,11 @@ pub struct dark_bwt_stats {
     pub emit_ms: f32,
     pub h2d_ms: f32,
     pub d2h_ms: f32,
+    pub gen_passes: u32,
+    pub gen_pass_ms: f32,
+    pub gen_elements: u64,
+    pub host_syncs: u32,
+    pub reserved_: u32,
 }
 
 extern "C" {

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_strerror(lib):
-    assert lib.dark_bwt_abi_version() == 1
+    assert lib.dark_bwt_abi_version() == 2
     msgs = {lib.dark_bwt_strerror(c).decode() for c in range(0, 7)}
     assert len(msgs) == 7 and "ok" in msgs
 

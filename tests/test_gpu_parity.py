@@ -166,7 +166,9 @@ FORCED_PATHS = [
     ({"DARK_BWT_SORT_VARIANT": "0"}, "mixed", 4, 700001),            # the other radix-pass tilings
     ({"DARK_BWT_SORT_VARIANT": "2"}, "mixed", 4, 700001),
     ({"DARK_BWT_SORT_VARIANT": "5"}, "dna", 1, 700001),
-    ({"DARK_BWT_TILE_BY_BLOCKIDX": "1"}, "mixed", 9, 900001),
+    ({"DARK_BWT_PASS_IMPL": "0"}, "mixed", 9, 900001),               # the round-1 pass kernel (fallback of unaligned inputs / digits)
+    ({"DARK_BWT_PASS_IMPL": "0"}, "dna", 7, 1000003),                # ... with its key-generating variant
+    ({"DARK_BWT_PASS_IMPL": "0", "DARK_BWT_FORCE_U64_STATUS": "1"}, "rep17", 5, 600007),
     ({"DARK_BWT_RANK_SEARCH": "0"}, "dna", 6, 1500003),              # selective rank fill (bitmap + SA sweep) instead of the search
     ({"DARK_BWT_SPARSE_RERANK": "0"}, "dna", 9, 1400003),            # pruned round 0 re-ranked by the scan kernel instead of the sparse path
     ({"DARK_BWT_PAIRS": "0"}, "mixed", 4, 1300001),
@@ -249,6 +251,14 @@ def test_emission_kernel_alone(saca, oracle, torch):
             origin = con.emit_device(dt.data_ptr(), n, ds.data_ptr(), db.data_ptr() + off)
             assert origin == origin_o
             assert np.array_equal(db.cpu().numpy()[off:off + n], bwt_o)
+        # a suffix array that is only 4-byte aligned (a slice of a larger buffer): no 128-bit SA loads
+        ds_off = torch.zeros(n + 4, dtype=torch.int32, device="cuda")
+        for shift in (1, 2, 3):
+            ds_off[shift:shift + n] = ds
+            db = torch.zeros(n + 8, dtype=torch.uint8, device="cuda")
+            origin = con.emit_device(dt.data_ptr(), n, ds_off.data_ptr() + 4 * shift, db.data_ptr())
+            assert origin == origin_o
+            assert np.array_equal(db.cpu().numpy()[:n], bwt_o)
         con.close()
 
 
@@ -343,6 +353,26 @@ def test_idempotent_context_reuse(saca, oracle, torch):
 
 
 # ---- the unpack side: inverse BWT ---------------------------------------------------
+@pytest.mark.parametrize("kind,seed,n", [("dna", 12, 500003), ("mixed", 13, 400001), ("text", 14, 300007), ("rep17", 15, 200003)])
+def test_device_entry_with_unaligned_buffers(saca, oracle, torch, kind, seed, n):
+    """d_text, d_bwt_out and d_sa_out may be arbitrary slices of larger device buffers: text and BWT at odd byte offsets,
+    the suffix array only 4-byte aligned (no 128-bit accesses may be assumed on any of them)."""
+    from dark_b200 import synth
+    t = synth.generate(kind, seed, n)
+    bwt_o, origin_o, sa_o = oracle.bwt_forward(t, want_sa=True)
+    con = saca.Constructor(n)
+    for toff, boff, soff in ((0, 0, 1), (1, 3, 3), (5, 2, 2)):
+        dt = torch.zeros(n + 16, dtype=torch.uint8, device="cuda")
+        dt[toff:toff + n] = torch.from_numpy(t).cuda()
+        db = torch.zeros(n + 16, dtype=torch.uint8, device="cuda")
+        ds = torch.zeros(n + 8, dtype=torch.int32, device="cuda")
+        origin = con.bwt_device(dt.data_ptr() + toff, n, db.data_ptr() + boff, ds.data_ptr() + 4 * soff)
+        assert origin == origin_o
+        assert np.array_equal(db.cpu().numpy()[boff:boff + n], bwt_o)
+        assert np.array_equal(ds.cpu().numpy()[soff:soff + n].view(np.uint32), sa_o)
+    con.close()
+
+
 def test_inverse_known_answers(saca, torch):
     # saca.rs:404-406: bwt::decode(&output, origin, suf) gives back the input of the KATs
     for text, _, origin, bwt in KAT:

@@ -16,7 +16,6 @@ m = 1 << lg
 g = torch.Generator(device="cuda").manual_seed(1)
 keys0 = torch.randint(0, 1 << 62, (m,), dtype=torch.int64, device="cuda", generator=g)
 vals0 = torch.arange(m, dtype=torch.int32, device="cuda")
-con = saca.Constructor(m, flags=_ffi.F_DEVICE_ONLY)
 ref_vals = None
 if m <= (1 << 27):
     torch.cuda.synchronize()
@@ -35,6 +34,7 @@ for v in variants:
         os.environ["DARK_BWT_PASS_IMPL"] = "0"
     elif v != "tma":
         os.environ["DARK_BWT_SORT_VARIANT"] = str(int(v))
+    con = saca.Constructor(m, flags=_ffi.F_DEVICE_ONLY)   # the knobs are read when the context is created
     best = None
     ok = True
     for rep in range(3):
@@ -51,4 +51,4 @@ for v in variants:
     # 8 passes of 24 B/pair + 8 B/pair histogram read
     print(json.dumps({"variant": v, "m": m, "ok": ok, "sort_ms": best, "ms_per_pass": best / 8,
                       "pass_GBs_incl_hist": (8 * 24 + 8) * m / best / 1e6}), flush=True)
-con.close()
+    con.close()
