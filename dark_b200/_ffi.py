@@ -17,7 +17,7 @@ SYMBOLS = [
     "dark_bwt_abi_version", "dark_bwt_create", "dark_bwt_create_ex", "dark_bwt_capacity", "dark_bwt_forward",
     "dark_bwt_forward_batch", "dark_bwt_forward_many", "dark_bwt_forward_many_device", "dark_bwt_forward_device", "dark_bwt_inverse", "dark_bwt_inverse_device", "dark_bwt_reuse", "dark_bwt_destroy", "dark_bwt_strerror", "dark_bwt_last_error",
     "dark_bwt_stream", "dark_bwt_sort_pairs_device", "dark_bwt_verify_sa_device", "dark_bwt_emit_device", "dark_bwt_lcp_profile_device",
-    "dark_bwt_synth",
+    "dark_bwt_synth", "dark_bwt_dc_encode_device", "dark_bwt_dc_encode", "dark_bwt_forward_dc",
 ]
 
 
@@ -42,6 +42,13 @@ class Stats(ctypes.Structure):
         d["active"] = [int(self.active[i]) for i in range(r + 1)]
         d["passes"] = [int(self.passes[i]) for i in range(r + 1)]
         return d
+
+
+class DcInfo(ctypes.Structure):
+    """dark_bwt_dc_info"""
+    _fields_ = [("init", ctypes.c_uint64 * 256), ("mtf_symbols", ctypes.c_uint8 * 256), ("num_unique", ctypes.c_uint32),
+                ("reserved_", ctypes.c_uint32), ("num_items", ctypes.c_uint64), ("device_ms", ctypes.c_float),
+                ("reserved2_", ctypes.c_uint32)]
 
 
 class DarkBwtError(RuntimeError):
@@ -101,6 +108,9 @@ def lib():
     L.dark_bwt_emit_device.argtypes = [vp, vp, u64, vp, vp, ctypes.POINTER(u64)]
     L.dark_bwt_lcp_profile_device.argtypes = [vp, vp, u64, vp, ctypes.POINTER(u64), ctypes.POINTER(u32), ctypes.POINTER(u64)]
     L.dark_bwt_synth.argtypes = [ctypes.c_char_p, u64, vp, u64]
+    L.dark_bwt_dc_encode_device.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, ctypes.POINTER(DcInfo)]
+    L.dark_bwt_dc_encode.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, ctypes.POINTER(DcInfo)]
+    L.dark_bwt_forward_dc.argtypes = [vp, vp, u64, vp, ctypes.POINTER(u64), vp, vp, vp, vp, vp, ctypes.POINTER(DcInfo), ctypes.POINTER(Stats)]
     _lib = L
     return L
 

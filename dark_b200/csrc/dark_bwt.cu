@@ -27,6 +27,7 @@
 #include "radix_sort.cuh"
 #include "onesweep_tma.cuh"
 #include "suffix_kernels.cuh"
+#include "dc_kernels.cuh"
 
 using namespace dark;
 
@@ -191,6 +192,7 @@ struct dark_bwt_ctx {
     u32* many_starts = nullptr;            // dark_bwt_forward_many: block offsets (kMaxManyBlocks + 1)
     unsigned long long* many_origins = nullptr;  // ... per-block origins
     u16* many_lut = nullptr;               // ... byte -> code 1..sigma
+    DcInfoDev* dc_info = nullptr;             // dark_bwt_dc_*: device copy of the result header, followed by the run counter
     u32* bitmap = nullptr;  // n bits: positions whose rank the next round reads
     size_t scan_tiles = 0;
 
@@ -1162,6 +1164,55 @@ int inverse_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, u64 origin64, u8
     return DARK_BWT_OK;
 }
 
+// Distance coding + MTF of a BWT block on device buffers (dc_kernels.cuh).  Every output pointer is nullable: the
+// context's own arena is used for what the caller does not want.  *d_dist_used / *d_pos_used etc. tell where the data is.
+struct DcBuffers {
+    u32* dist = nullptr;     // n
+    u32* item_pos = nullptr; // num_items
+    u32* item_dist = nullptr;
+    u8* item_sym = nullptr;
+    u8* item_rank = nullptr;
+};
+int dc_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, DcBuffers* io, dark_bwt_dc_info* info) {
+    if (n64 < 1 || n64 > ctx->capacity || n64 > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;
+    const u32 n = (u32)n64;
+    CK(cudaSetDevice(ctx->device));
+    const u32 nblocks = (u32)ceil_div(n, kDcBlock);
+    u32* tab = ctx->ranks;  // nblocks x 256 words = n/4 bytes
+    u32* run_counts = ctx->ranks_alt;
+    u32* first = ctx->bucket_hist;
+    u32* final_last = ctx->bucket_hist + 256;
+    if (!io->dist) io->dist = (u32*)ctx->keys[0];
+    if (!io->item_pos) io->item_pos = ctx->isa;
+    if (!io->item_dist) io->item_dist = ctx->sa;
+    u32* run_start = ctx->ids[0];
+    if (!io->item_sym) io->item_sym = (u8*)ctx->ids[1];
+    if (!io->item_rank) io->item_rank = (u8*)ctx->ids[1] + align_up((size_t)n, 256);
+    unsigned long long* total_runs = (unsigned long long*)((char*)ctx->dc_info + align_up(sizeof(DcInfoDev), 8));
+    cudaEvent_t ea = ctx->events[kMaxEvents - 1], eb = ctx->events[kMaxEvents - 2];
+    CK(cudaEventRecord(ea, ctx->stream));
+    CK(cudaMemsetAsync(first, 0xFF, sizeof(u32) * 256, ctx->stream));
+    CK(cudaMemsetAsync(total_runs, 0, sizeof(unsigned long long), ctx->stream));
+    k_dc_tables<<<nblocks, 256, 0, ctx->stream>>>(d_bwt, n, tab, first, run_counts, io->dist, total_runs);
+    LAUNCHED();
+    k_dc_scan<<<1, 256, 0, ctx->stream>>>(tab, nblocks, final_last);
+    LAUNCHED();
+    k_sparse_scan<<<1, 1024, 0, ctx->stream>>>(run_counts, nblocks);  // in place: exclusive run offsets
+    LAUNCHED();
+    k_dc_ranks<<<(u32)ceil_div(nblocks, 8), 256, 0, ctx->stream>>>(d_bwt, n, tab, run_counts, nblocks, io->dist, run_start, io->item_sym, io->item_rank);
+    LAUNCHED();
+    k_dc_final<<<1, 256, 0, ctx->stream>>>(n, final_last, first, io->dist, total_runs, ctx->dc_info);
+    LAUNCHED();
+    k_dc_stream<<<(u32)std::min<u64>(ceil_div(n, 256), (u64)ctx->num_sms * 16), 256, 0, ctx->stream>>>(run_start, total_runs, n, io->dist, io->item_pos, io->item_dist);
+    LAUNCHED();
+    CK(cudaEventRecord(eb, ctx->stream));
+    static_assert(offsetof(dark_bwt_dc_info, num_items) == offsetof(DcInfoDev, num_items), "DcInfoDev mirrors the head of dark_bwt_dc_info");
+    CK(cudaMemcpyAsync(info, ctx->dc_info, sizeof(DcInfoDev), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&info->device_ms, ea, eb);
+    return DARK_BWT_OK;
+}
+
 // ---- pageable host buffers ---------------------------------------------------------------------
 bool is_pageable(const void* p) {
     cudaPointerAttributes a;
@@ -1330,6 +1381,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     const size_t o_mstarts = carve(sizeof(u32) * (kMaxManyBlocks + 1));
     const size_t o_morigins = carve(sizeof(unsigned long long) * kMaxManyBlocks);
     const size_t o_mlut = carve(sizeof(u16) * 256);
+    const size_t o_dcinfo = carve(sizeof(DcInfoDev) + 16);
     ctx->arena_bytes = off;
 
     auto bail = [&](int code) {
@@ -1366,6 +1418,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     ctx->many_starts = (u32*)(base + o_mstarts);
     ctx->many_origins = (unsigned long long*)(base + o_morigins);
     ctx->many_lut = (u16*)(base + o_mlut);
+    ctx->dc_info = (DcInfoDev*)(base + o_dcinfo);
 
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DARK_BWT_E_CUDA);
     if (staging) {
@@ -1614,6 +1667,67 @@ int dark_bwt_inverse(dark_bwt_ctx* ctx, const uint8_t* bwt, uint64_t n, uint64_t
     if (int rc = copy_in_blocking(ctx, ctx->d_bwt, bwt, n, ctx->stream)) return rc;
     if (int rc = inverse_device(ctx, ctx->d_bwt, n, origin, ctx->d_text, nullptr)) return rc;
     return copy_out_blocking(ctx, text_out, ctx->d_text, n, ctx->stream);
+}
+
+int dark_bwt_dc_encode_device(dark_bwt_ctx* ctx, const uint8_t* d_bwt, uint64_t n, uint32_t* d_dist_out, uint32_t* d_item_pos,
+                              uint32_t* d_item_dist, uint8_t* d_item_sym, uint8_t* d_item_rank, dark_bwt_dc_info* info) {
+    if (!ctx || !d_bwt || !info) return DARK_BWT_E_INVALID_ARG;
+    ctx->err[0] = 0;
+    DcBuffers io;
+    io.dist = d_dist_out;
+    io.item_pos = d_item_pos;
+    io.item_dist = d_item_dist;
+    io.item_sym = d_item_sym;
+    io.item_rank = d_item_rank;
+    return dc_device(ctx, d_bwt, n, &io, info);
+}
+
+// host buffers; ctx->d_bwt already holds the block when `bwt` is null (dark_bwt_forward_dc)
+static int dc_host(dark_bwt_ctx* ctx, const uint8_t* bwt, uint64_t n, uint32_t* dist_out, uint32_t* item_pos, uint32_t* item_dist,
+                   uint8_t* item_sym, uint8_t* item_rank, dark_bwt_dc_info* info) {
+    if (bwt)
+        if (int rc = copy_in_blocking(ctx, ctx->d_bwt, bwt, n, ctx->stream)) return rc;
+    DcBuffers io;
+    if (int rc = dc_device(ctx, ctx->d_bwt, n, &io, info)) return rc;
+    const size_t items = (size_t)info->num_items;
+    if (dist_out)
+        if (int rc = copy_out_blocking(ctx, dist_out, io.dist, n * sizeof(u32), ctx->stream)) return rc;
+    if (item_pos && items)
+        if (int rc = copy_out_blocking(ctx, item_pos, io.item_pos, items * sizeof(u32), ctx->stream)) return rc;
+    if (item_dist && items)
+        if (int rc = copy_out_blocking(ctx, item_dist, io.item_dist, items * sizeof(u32), ctx->stream)) return rc;
+    if (item_sym && items)
+        if (int rc = copy_out_blocking(ctx, item_sym, io.item_sym, items, ctx->stream)) return rc;
+    if (item_rank && items)
+        if (int rc = copy_out_blocking(ctx, item_rank, io.item_rank, items, ctx->stream)) return rc;
+    return DARK_BWT_OK;
+}
+
+int dark_bwt_dc_encode(dark_bwt_ctx* ctx, const uint8_t* bwt, uint64_t n, uint32_t* dist_out, uint32_t* item_pos, uint32_t* item_dist,
+                       uint8_t* item_sym, uint8_t* item_rank, dark_bwt_dc_info* info) {
+    if (!ctx || !bwt || !info) return DARK_BWT_E_INVALID_ARG;
+    if (ctx->flags & DARK_BWT_F_DEVICE_ONLY) return DARK_BWT_E_INVALID_ARG;
+    if (n < 1 || n > ctx->capacity || n > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;
+    ctx->err[0] = 0;
+    CK(cudaSetDevice(ctx->device));
+    return dc_host(ctx, bwt, n, dist_out, item_pos, item_dist, item_sym, item_rank, info);
+}
+
+int dark_bwt_forward_dc(dark_bwt_ctx* ctx, const uint8_t* text, uint64_t n, uint8_t* bwt_out, uint64_t* origin_out, uint32_t* dist_out,
+                        uint32_t* item_pos, uint32_t* item_dist, uint8_t* item_sym, uint8_t* item_rank, dark_bwt_dc_info* info,
+                        dark_bwt_stats* stats) {
+    if (!ctx || !text || !origin_out || !info) return DARK_BWT_E_INVALID_ARG;
+    if (ctx->flags & DARK_BWT_F_DEVICE_ONLY) return DARK_BWT_E_INVALID_ARG;
+    if (n < 2 || n > ctx->capacity || n > 0xFFFFFFFEull) return DARK_BWT_E_INVALID_N;
+    ctx->err[0] = 0;
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = copy_in_blocking(ctx, ctx->d_text, text, n, ctx->stream)) return rc;
+    if (stats) stats->h2d_ms = 0.f;
+    if (int rc = forward_device(ctx, ctx->d_text, n, ctx->d_bwt, origin_out, nullptr, stats)) return rc;
+    if (bwt_out)
+        if (int rc = copy_out_blocking(ctx, bwt_out, ctx->d_bwt, n, ctx->stream)) return rc;
+    // the BWT is still in HBM: distance coding reads it there
+    return dc_host(ctx, nullptr, n, dist_out, item_pos, item_dist, item_sym, item_rank, info);
 }
 
 int dark_bwt_reuse(dark_bwt_ctx* ctx, uint32_t** words_out, uint64_t* count_out) {

@@ -153,6 +153,47 @@ class Constructor:
                    "bwt::decode")
         return float(ms.value)
 
+    # -- distance coding + MTF: bwt::dc::encode(&output, suf, &mut mtf) and its item stream (block/dc.rs:52, 82-85) ---------
+    def _dc_result(self, info, n, dist, pos, idist, sym, rank):
+        k = int(info.num_items)
+        return {"dist": dist, "init": np.array(list(info.init), dtype=np.uint64), "mtf_symbols": np.array(list(info.mtf_symbols), dtype=np.uint8),
+                "num_unique": int(info.num_unique), "num_items": k, "item_pos": pos[:k], "item_dist": idist[:k], "item_sym": sym[:k],
+                "item_rank": rank[:k], "device_ms": float(info.device_ms)}
+
+    def dc_encode(self, bwt, want_dist=True):
+        """Distance coding of a BWT block (host buffers): dict(dist u32[n] with filler n, init[256], mtf_symbols, num_unique,
+        and the (distance, Context) items: item_pos/item_dist/item_sym/item_rank)."""
+        b = _as_u8(bwt)
+        n = b.size
+        dist = np.empty(n, dtype=np.uint32) if want_dist else None
+        pos, idist = np.empty(n, dtype=np.uint32), np.empty(n, dtype=np.uint32)
+        sym, rank = np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.uint8)
+        info = _ffi.DcInfo()
+        _ffi.check(self._L.dark_bwt_dc_encode(self._ctx, b.ctypes.data, n, dist.ctypes.data if want_dist else None, pos.ctypes.data,
+                                              idist.ctypes.data, sym.ctypes.data, rank.ctypes.data, ctypes.byref(info)), self._ctx, "dc::encode")
+        return self._dc_result(info, n, dist, pos, idist, sym, rank)
+
+    def bwt_dc(self, input, want_dist=True):
+        """block/dc.rs:45-52 in one call: (bwt, origin, dc dict) — the DC stage reads the BWT while it is still in HBM."""
+        t = _as_u8(input)
+        n = t.size
+        out = np.empty(n, dtype=np.uint8)
+        dist = np.empty(n, dtype=np.uint32) if want_dist else None
+        pos, idist = np.empty(n, dtype=np.uint32), np.empty(n, dtype=np.uint32)
+        sym, rank = np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.uint8)
+        info, origin = _ffi.DcInfo(), ctypes.c_uint64(0)
+        _ffi.check(self._L.dark_bwt_forward_dc(self._ctx, t.ctypes.data, n, out.ctypes.data, ctypes.byref(origin),
+                                               dist.ctypes.data if want_dist else None, pos.ctypes.data, idist.ctypes.data, sym.ctypes.data,
+                                               rank.ctypes.data, ctypes.byref(info), ctypes.byref(self.stats)), self._ctx, "bwt + dc::encode")
+        return out, int(origin.value), self._dc_result(info, n, dist, pos, idist, sym, rank)
+
+    def dc_encode_device(self, d_bwt, n, d_dist=None, d_item_pos=None, d_item_dist=None, d_item_sym=None, d_item_rank=None):
+        """Device pointers in, device pointers out (all outputs optional); returns the DcInfo header."""
+        info = _ffi.DcInfo()
+        _ffi.check(self._L.dark_bwt_dc_encode_device(self._ctx, d_bwt, int(n), d_dist, d_item_pos, d_item_dist, d_item_sym, d_item_rank,
+                                                     ctypes.byref(info)), self._ctx, "dc::encode")
+        return info
+
     # -- device-resident form (benches, pipelines that keep the block in HBM) ------------------
     def bwt_device(self, d_text, n, d_bwt, d_sa=None):
         """Raw device pointers (ints).  Returns origin; self.stats holds the device timings."""

@@ -149,6 +149,40 @@ int dark_bwt_inverse(dark_bwt_ctx *ctx, const uint8_t *bwt, uint64_t n, uint64_t
 int dark_bwt_inverse_device(dark_bwt_ctx *ctx, const uint8_t *d_bwt, uint64_t n, uint64_t origin, uint8_t *d_text_out,
                             float *ms_out /* nullable */);
 
+/* ---- distance coding + MTF ---------------------------------------------------------------
+ * What `bwt::dc::encode(&output, suf, &mut self.mtf)` computes and what iterating its result yields
+ * (/root/reference/src/block/dc.rs:52, 54-85).  That code is third-party (`compress::bwt::dc`, Cargo.toml:18) and absent
+ * from the reference tree, and no reference test holds a known answer for it: PARITY UNPINNED (checked against a
+ * CPU restatement of upstream rust-compress in the test suite and by encode -> decode round trips).
+ *   dist[i]  = n (the filler) unless i is the last byte of a run; then next_occurrence - i - rank - 1, rank = the MTF rank
+ *              of the symbol at its next occurrence (= distinct symbols in between); for a symbol's last run
+ *              n - i - final rank - 1.  This is the `distances` slice the reference passes in as `suf` (block/dc.rs:51).
+ *   items    = one (distance, Context) per run, in order: item_pos = run end (Context.distance_limit = n - item_pos),
+ *              item_dist, item_sym = Context.symbol, item_rank = Context.last_rank.  */
+typedef struct dark_bwt_dc_info {
+    uint64_t init[256];       /* get_init(): first occurrence of each byte value, n if it does not occur */
+    uint8_t mtf_symbols[256]; /* the MTF list after the block: the num_unique symbols by recency, then the absent ones */
+    uint32_t num_unique;
+    uint32_t reserved_;
+    uint64_t num_items;       /* runs of equal bytes = (distance, Context) items */
+    float device_ms;          /* CUDA-event time of the DC kernels */
+    uint32_t reserved2_;
+} dark_bwt_dc_info;
+
+/* Device buffers.  d_dist_out (n words) and the four item arrays (room for n entries each) are nullable: what the caller
+ * does not ask for stays in the context's arena.  1 <= n <= capacity. */
+int dark_bwt_dc_encode_device(dark_bwt_ctx *ctx, const uint8_t *d_bwt, uint64_t n, uint32_t *d_dist_out, uint32_t *d_item_pos,
+                              uint32_t *d_item_dist, uint8_t *d_item_sym, uint8_t *d_item_rank, dark_bwt_dc_info *info);
+/* Host buffers (pageable or pinned); every output but `info` nullable.  The item arrays need room for n entries
+ * (info->num_items are written). */
+int dark_bwt_dc_encode(dark_bwt_ctx *ctx, const uint8_t *bwt, uint64_t n, uint32_t *dist_out, uint32_t *item_pos,
+                       uint32_t *item_dist, uint8_t *item_sym, uint8_t *item_rank, dark_bwt_dc_info *info);
+/* block/dc.rs:45-52 in one call: forward BWT of text[0..n), then distance coding of the BWT while it is still in HBM.
+ * bwt_out and the DC outputs are nullable (a caller that codes the item stream needs neither bwt_out nor dist_out). */
+int dark_bwt_forward_dc(dark_bwt_ctx *ctx, const uint8_t *text, uint64_t n, uint8_t *bwt_out, uint64_t *origin_out,
+                        uint32_t *dist_out, uint32_t *item_pos, uint32_t *item_dist, uint8_t *item_sym, uint8_t *item_rank,
+                        dark_bwt_dc_info *info, dark_bwt_stats *stats);
+
 /* Constructor::reuse — lends >= capacity host u32 words of scratch (DC distances in
  * block/dc.rs:51).  Allocated on first use; owned by the context. */
 int dark_bwt_reuse(dark_bwt_ctx *ctx, uint32_t **words_out, uint64_t *count_out);

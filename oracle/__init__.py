@@ -171,3 +171,44 @@ class Arena:
         lib().oracle_bwt_emit(t.ctypes.data, t.size, self.arena.ctypes.data, self.bwt.ctypes.data,
                               ctypes.byref(origin))
         return self.bwt, origin.value
+
+
+# ---- distance coding + MTF (dc_oracle.c): PARITY UNPINNED, restated from memory of upstream rust-compress ------------
+def dc_encode(bwt):
+    """`bwt::dc::encode(&output, suf, &mut mtf)`: (distances u32[n] with filler n, init[256], mtf_symbols[256], num_unique)."""
+    b = _u8(bwt)
+    L = lib()
+    dist = np.empty(b.size, dtype=np.uint32)
+    init = (ctypes.c_uint64 * 256)()
+    mtf = (ctypes.c_uint8 * 256)()
+    nu = ctypes.c_uint32(0)
+    L.oracle_dc_encode.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32)]
+    _check(L.oracle_dc_encode(b.ctypes.data, b.size, dist.ctypes.data, init, mtf, ctypes.byref(nu)), "dc::encode")
+    return dist, np.array(list(init), dtype=np.uint64), np.array(list(mtf), dtype=np.uint8), int(nu.value)
+
+
+def dc_stream(bwt, dist, init):
+    """The (distance, Context) items the reference's EncodeIterator yields: (pos, dist, symbol, last_rank) arrays;
+    distance_limit = n - pos."""
+    b = _u8(bwt)
+    L = lib()
+    n = b.size
+    pos, d = np.empty(n, dtype=np.uint32), np.empty(n, dtype=np.uint32)
+    sym, rk = np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.uint8)
+    ini = (ctypes.c_uint64 * 256)(*[int(x) for x in init])
+    L.oracle_dc_stream.restype = ctypes.c_uint64
+    L.oracle_dc_stream.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p] + [ctypes.c_void_p] * 4
+    dd = np.ascontiguousarray(dist, dtype=np.uint32)
+    c = L.oracle_dc_stream(b.ctypes.data, dd.ctypes.data, n, ini, pos.ctypes.data, d.ctypes.data, sym.ctypes.data, rk.ctypes.data)
+    return pos[:c].copy(), d[:c].copy(), sym[:c].copy(), rk[:c].copy()
+
+
+def dc_decode(init, stream_dist, n):
+    """`bwt::dc::decode(init, &mut out, &mut mtf, |ctx| next distance)` collected."""
+    L = lib()
+    out = np.empty(n, dtype=np.uint8)
+    ini = (ctypes.c_uint64 * 256)(*[int(x) for x in init])
+    sd = np.ascontiguousarray(stream_dist, dtype=np.uint32)
+    L.oracle_dc_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64]
+    _check(L.oracle_dc_decode(ini, sd.ctypes.data, sd.size, out.ctypes.data, n), "dc::decode")
+    return out

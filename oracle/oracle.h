@@ -96,6 +96,14 @@ typedef struct {
 } oracle_profile;
 int oracle_profile_lcp(const uint8_t *text, uint64_t n, const uint32_t *sa, oracle_profile *out);
 
+/* ---- distance coding + MTF (dc_oracle.c; third-party `compress::bwt::dc`, PARITY UNPINNED: restated from memory of
+ * upstream rust-compress, no reference-held vector exists; call sites /root/reference/src/block/dc.rs:52,54-85,146) ---- */
+int oracle_dc_encode(const uint8_t *input, uint64_t n, uint32_t *distances, uint64_t init[256], uint8_t mtf_symbols[256],
+                     uint32_t *num_unique_out);
+uint64_t oracle_dc_stream(const uint8_t *input, const uint32_t *distances, uint64_t n, const uint64_t init[256], uint32_t *out_pos,
+                          uint32_t *out_dist, uint8_t *out_sym, uint8_t *out_rank);
+int oracle_dc_decode(const uint64_t init[256], const uint32_t *stream_dist, uint64_t count, uint8_t *output, uint64_t n);
+
 #ifdef __cplusplus
 }
 #endif

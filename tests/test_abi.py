@@ -58,6 +58,25 @@ def test_stats_struct_layout_matches_header():
     assert vals[1:] == [getattr(_ffi.Stats, f).offset for f in fields]
 
 
+def test_dc_info_struct_layout_matches_header():
+    import subprocess
+    import tempfile
+    from dark_b200 import _ffi
+    fields = [f for f, _ in _ffi.DcInfo._fields_]
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "dark_bwt.h"\nint main(){printf("%zu", sizeof(dark_bwt_dc_info));\n'
+    for f in fields:
+        prog += f'printf(" %zu", offsetof(dark_bwt_dc_info, {f}));\n'
+    prog += "return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(prog)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, c])
+        vals = [int(x) for x in subprocess.check_output([exe], text=True).split()]
+    assert vals[0] == ctypes.sizeof(_ffi.DcInfo)
+    assert vals[1:] == [getattr(_ffi.DcInfo, f).offset for f in fields]
+
+
 def test_null_arguments_are_rejected_before_any_device_work(lib):
     """Argument checks of the entry points run before anything touches CUDA: DARK_BWT_E_INVALID_ARG (2), no crash."""
     from dark_b200 import _ffi

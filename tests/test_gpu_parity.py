@@ -700,3 +700,62 @@ def test_sparse_rerank_fallbacks(saca, oracle, torch):
             bwt, origin, sa = con.bwt_and_sa(t)
             assert con.stats.initial_symbols < con.stats.symbols_per_key  # the initial sort was pruned
         assert origin == origin_o and np.array_equal(sa, sa_o) and np.array_equal(bwt, bwt_o)
+
+
+# ---- distance coding + MTF on the GPU (parity UNPINNED: checked against the restated oracle) ---------
+def _check_dc(res, b, oracle):
+    n = b.size
+    dist, init, mtf, nu = oracle.dc_encode(b)
+    pos, sd, sym, rk = oracle.dc_stream(b, dist, init)
+    assert res["num_unique"] == nu and res["num_items"] == pos.size
+    assert np.array_equal(res["init"], init)
+    assert np.array_equal(res["mtf_symbols"][:nu], mtf[:nu])
+    if res["dist"] is not None:
+        assert np.array_equal(res["dist"], dist)
+    assert np.array_equal(res["item_pos"], pos) and np.array_equal(res["item_dist"], sd)
+    assert np.array_equal(res["item_sym"], sym) and np.array_equal(res["item_rank"], rk)
+    assert np.array_equal(oracle.dc_decode(res["init"], res["item_dist"], n), b)      # and back
+
+
+@pytest.mark.gpu
+def test_dc_small_random_and_structured(saca, oracle, torch):
+    rng = np.random.default_rng(11)
+    con = saca.Constructor(1 << 16)
+    cases = [np.zeros(1, np.uint8), np.zeros(5000, np.uint8), np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8)[::-1].copy(),
+             np.tile(np.arange(256, dtype=np.uint8), 40), np.repeat(np.arange(7, dtype=np.uint8), 4099)[:20000],
+             np.frombuffer(b"rdarcaaaabb", dtype=np.uint8).copy(), np.frombuffer(b"nnbaaa", dtype=np.uint8).copy()]
+    for trial in range(120):
+        n = int(rng.integers(1, 9000))
+        sigma = int(rng.choice([1, 2, 4, 26, 256]))
+        b = rng.integers(0, sigma, n).astype(np.uint8)
+        if trial % 2:
+            b = np.repeat(b, rng.integers(1, 40, n))[: int(rng.integers(1, 60000))]
+        cases.append(b)
+    for b in cases:
+        _check_dc(con.dc_encode(b), b, oracle)
+    con.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,seed,n", [("text", 3, 768771), ("dna", 1, 1 << 20), ("mixed", 4, 1 << 22), ("rep17", 2, 1 << 20)])
+def test_forward_dc_fused_entry(saca, oracle, torch, kind, seed, n):
+    """block/dc.rs:45-52 in one call: forward BWT, then DC of the BWT while it is still in HBM; host buffers out."""
+    from dark_b200 import synth
+    t = synth.generate(kind, seed, n)
+    con = saca.Constructor(n)
+    bwt, origin, res = con.bwt_dc(t)
+    bwt_o, origin_o = oracle.bwt_forward(t)
+    assert origin == origin_o and np.array_equal(bwt, bwt_o)
+    _check_dc(res, bwt_o, oracle)
+    # device entry with caller-owned outputs
+    db = torch.from_numpy(bwt_o).cuda()
+    dd = torch.empty(n, dtype=torch.int32, device="cuda")
+    dpos, ddist = torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")
+    dsym, drk = torch.empty(n, dtype=torch.uint8, device="cuda"), torch.empty(n, dtype=torch.uint8, device="cuda")
+    info = con.dc_encode_device(db.data_ptr(), n, dd.data_ptr(), dpos.data_ptr(), ddist.data_ptr(), dsym.data_ptr(), drk.data_ptr())
+    k = int(info.num_items)
+    assert k == res["num_items"]
+    assert np.array_equal(dd.cpu().numpy().view(np.uint32), res["dist"])
+    assert np.array_equal(dpos.cpu().numpy().view(np.uint32)[:k], res["item_pos"])
+    assert np.array_equal(drk.cpu().numpy()[:k], res["item_rank"])
+    con.close()

@@ -194,3 +194,56 @@ def test_survey_origin_regressions(golden):
                         ("mixed:4:268435456", 70304439)):
         if key in golden:
             assert golden[key]["origin"] == origin
+
+
+# ---- distance coding + MTF (third-party compress::bwt::dc — PARITY UNPINNED) ------------------------
+def _dc_by_definition(b):
+    """distances straight from the definition in oracle/dc_oracle.c's header: slow, independent of the MTF list."""
+    b = list(b)
+    n = len(b)
+    dist, init, last = [n] * n, [n] * 256, {}
+    for i, s in enumerate(b):
+        if s in last:
+            base = last[s]
+            rank = len(set(b[base + 1:i]))
+            if rank > 0:
+                dist[base] = i - base - rank - 1
+        else:
+            init[s] = i
+        last[s] = i
+    for s, base in last.items():
+        dist[base] = n - base - len(set(b[base + 1:])) - 1
+    return dist, init
+
+
+def test_dc_oracle_matches_its_definition_and_round_trips(oracle):
+    """The DC restatement (unpinned: the crate is absent) is at least self-consistent: the MTF-list form equals the
+    set-based definition, every run end and nothing else carries a distance, the item ranks are the MTF ranks a decoder
+    can know, and dc::decode restores the block from init + the distance stream."""
+    rng = np.random.default_rng(7)
+    for trial in range(1500):
+        n = int(rng.integers(1, 80))
+        sigma = int(rng.choice([1, 2, 3, 4, 26, 256]))
+        b = rng.integers(0, sigma, n).astype(np.uint8)
+        if trial % 3 == 0:
+            b = np.repeat(b, rng.integers(1, 5, n))
+        n = b.size
+        dist, init, mtf, nu = oracle.dc_encode(b)
+        d0, i0 = _dc_by_definition(b)
+        assert list(dist) == d0 and list(init) == i0
+        assert nu == len(set(b.tolist()))
+        run_end = np.ones(n, dtype=bool)
+        run_end[:-1] = b[:-1] != b[1:]
+        assert np.array_equal(dist != n, run_end) or n == 0
+        pos, sd, sym, rk = oracle.dc_stream(b, dist, init)
+        assert np.array_equal(pos, np.flatnonzero(run_end)) and np.array_equal(sym, b[pos])
+        assert np.array_equal(oracle.dc_decode(init, sd, n), b)
+
+
+def test_dc_oracle_on_a_real_bwt(oracle):
+    t = oracle.gen("text", 3, 50000)
+    bwt, origin = oracle.bwt_forward(t)
+    dist, init, mtf, nu = oracle.dc_encode(bwt)
+    pos, sd, sym, rk = oracle.dc_stream(bwt, dist, init)
+    assert pos.size < bwt.size // 2                      # a BWT of text has long runs: that is what DC feeds on
+    assert np.array_equal(oracle.dc_decode(init, sd, bwt.size), bwt)
