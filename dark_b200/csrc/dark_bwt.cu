@@ -93,6 +93,8 @@ struct Knobs {
     bool check_hist = false;        // DARK_BWT_CHECK_HIST=1 counts both ways and compares
     bool inline_emit = true;        // DARK_BWT_INLINE_EMIT=0
     bool sparse_rerank = true;      // DARK_BWT_SPARSE_RERANK=0
+    bool rerank_chainfree = false;  // DARK_BWT_RERANK_CHAINFREE=1: rounds >= 1 re-ranked by flags + scan + apply kernels (no look-back chain; measured
+                                    // equal to the single kernel on C3/C5/C4: profiles/r2_rejected.md)
     int text_div = 8;               // DARK_BWT_TEXT_BUILD=<k>: text-order key build while m > n/k (0 = never, no isa[] tag)
     bool pairs = true;              // DARK_BWT_PAIRS=0
     bool rank_search = true;        // DARK_BWT_RANK_SEARCH=0
@@ -121,6 +123,7 @@ struct Knobs {
         check_hist = geti("DARK_BWT_CHECK_HIST", 0) != 0;
         inline_emit = geti("DARK_BWT_INLINE_EMIT", 1) != 0;
         sparse_rerank = geti("DARK_BWT_SPARSE_RERANK", 1) != 0;
+        rerank_chainfree = geti("DARK_BWT_RERANK_CHAINFREE", 0) != 0;
         text_div = geti("DARK_BWT_TEXT_BUILD", text_div);
         pairs = geti("DARK_BWT_PAIRS", 1) != 0;
         rank_search = geti("DARK_BWT_RANK_SEARCH", 1) != 0;
@@ -193,7 +196,8 @@ struct dark_bwt_ctx {
     unsigned long long* many_origins = nullptr;  // ... per-block origins
     u16* many_lut = nullptr;               // ... byte -> code 1..sigma
     DcInfoDev* dc_info = nullptr;             // dark_bwt_dc_*: device copy of the result header, followed by the run counter
-    u32* bitmap = nullptr;  // n bits: positions whose rank the next round reads
+    u32* bitmap = nullptr;  // n bits: positions whose rank the next round reads; new-head flags of the chain-free re-rank
+    u32* bitmap2 = nullptr;  // old-head flags of the chain-free re-rank
     size_t scan_tiles = 0;
 
     Mailbox* mail = nullptr;      // pinned + mapped host memory: kernels write their scalar results straight into it
@@ -349,6 +353,10 @@ int launch_pass_tma(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout
 #ifndef DARK_PASS_ILP
 #define DARK_PASS_ILP 2
 #endif
+#ifndef DARK_PASS_THREADS
+#define DARK_PASS_THREADS 256
+#define DARK_PASS_ITEMS 16
+#endif
 constexpr int kDefaultSortVariant = 1;  // 256 threads x 16 items, 3 CTAs/SM: best of the sweeps in profiles/r1_sort_variants_*.log
 
 // One onesweep pass over m pairs: buffers[cur] -> buffers[cur^1].
@@ -371,7 +379,7 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
         const bool eligible = (shift & 7) == 0 && !ev && (gen == nullptr || gen->mode == 0) &&
                               (gen != nullptr || (prev_text == nullptr && ((uintptr_t)kin & 15) == 0 && ((uintptr_t)vin & 15) == 0));
         if (impl != 0 && eligible) {
-            return launch_pass_tma<256, 16, 2, DARK_PASS_ILP>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, gen);
+            return launch_pass_tma<DARK_PASS_THREADS, DARK_PASS_ITEMS, 2, DARK_PASS_ILP>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, gen);
         }
     }
     if (gen != nullptr) return launch_pass_variant<256, 16, 3, 2>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, n_text, gen);
@@ -469,19 +477,42 @@ int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32
                   const u8* text, u8* bwt_inline, PairSink sink = PairSink()) {
     const u32 tiles = (u32)ceil_div(m, kScanTile);
     if (tiles > ctx->scan_tiles) return ctx->fail_internal("scan tile state too small");
+    ScanTileState ts{ctx->scan_words};
+    constexpr size_t smem = (size_t)kScanTile * 8;
+    if (!ROUND0 && ctx->knobs.rerank_chainfree) {
+        // rounds >= 1: flags + tile aggregates, a scan over the aggregates, apply — no chain between tiles (suffix_kernels.cuh)
+        auto kflags = k_rerank<kScanThreads, kScanItems, false, false, 1>;
+        auto kapply = k_rerank<kScanThreads, kScanItems, false, PAIRS, 2>;
+        if (smem > 48 * 1024) {
+            CK(cudaFuncSetAttribute(kflags, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(kapply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        u8* fnew = (u8*)ctx->bitmap;
+        u8* fold = (u8*)ctx->bitmap2;
+        kflags<<<tiles, kScanThreads, 0, ctx->stream>>>(keys, ids, ctx->ranks, m, n, K, kb, ctx->isa, sa, out_ids, ctx->ranks_alt, ts, nullptr,
+                                                           &ctx->mail_dev->count, nullptr, nullptr, nullptr, 0, text, bwt_inline,
+                                                           &ctx->mail_dev->origin, 0u, ctx->tag, nullptr, fnew, fold);
+        LAUNCHED();
+        k_rerank_scan_tiles<<<1, 1024, 0, ctx->stream>>>(ctx->scan_words, tiles, &ctx->mail_dev->count);
+        LAUNCHED();
+        kapply<<<tiles, kScanThreads, smem, ctx->stream>>>(keys, ids, ctx->ranks, m, n, K, kb, ctx->isa, sa, out_ids, ctx->ranks_alt, ts, nullptr,
+                                                           &ctx->mail_dev->count, sink.ids, sink.vals, ctx->bucket_hist, sink.shift, text, bwt_inline,
+                                                           &ctx->mail_dev->origin, 0u, ctx->tag, nullptr, fnew, fold);
+        LAUNCHED();
+        std::swap(ctx->ranks, ctx->ranks_alt);
+        return 0;
+    }
     u32* counter = nullptr;
     if (int rc = next_counter(ctx, &counter)) return rc;
     CK(cudaMemsetAsync(ctx->scan_words, 0, sizeof(u64) * kScanWordsPerTile * tiles, ctx->stream));
-    ScanTileState ts{ctx->scan_words};
     const u32 prefetch_ahead = ctx->knobs.rerank_prefetch >= 0 ? (u32)ctx->knobs.rerank_prefetch : 2u * (u32)ctx->num_sms;  // one wave of CTAs ahead (-2 %)
     auto kern = k_rerank<kScanThreads, kScanItems, ROUND0, PAIRS>;
-    constexpr size_t smem = (size_t)kScanTile * 8;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<tiles, kScanThreads, smem, ctx->stream>>>(
         keys, ids, ROUND0 ? nullptr : ctx->ranks, m, n, K, kb, ctx->isa, sa, out_ids, ROUND0 ? ctx->ranks : ctx->ranks_alt, ts, counter,
         &ctx->mail_dev->count, sink.ids, sink.vals,
         ctx->bucket_hist, sink.shift, text, bwt_inline, &ctx->mail_dev->origin, prefetch_ahead, ROUND0 ? 0u : ctx->tag,
-        ROUND0 ? ctx->rerank_trace : nullptr);
+        ROUND0 ? ctx->rerank_trace : nullptr, nullptr, nullptr);
     LAUNCHED();
     if (!ROUND0) std::swap(ctx->ranks, ctx->ranks_alt);
     return 0;
@@ -506,6 +537,8 @@ int region_scatter(dark_bwt_ctx* ctx, const u32* ids, const u32* vals, u32 upper
     u32* chunk_prefix = ctx->bucket_hist + 256;
     k_region_chunks<<<1, 256, 0, ctx->stream>>>(ctx->bucket_hist, chunk_prefix);
     LAUNCHED();
+    // one CTA per chunk, dispatched in chunk order: the chunks in flight stay neighbours, so they write one bucket's slice of
+    // isa[] while it sits in L2 (persistent CTAs striding over the chunks drift apart: C5 re-rank phase 9.6 -> 17.6 ms)
     k_scatter_regions<<<(u32)ceil_div(upper, kRegionChunk) + 256, 256, 0, ctx->stream>>>(ids, vals, ctx->bucket_hist, chunk_prefix, shift, ctx->isa);
     LAUNCHED();
     return 0;
@@ -1376,7 +1409,8 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     const size_t o_status = carve(ctx->sort_status_bytes);
     const size_t o_counters = carve(sizeof(u32) * kMaxCounters);
     const size_t o_bhist = carve(sizeof(u32) * 1024);  // 256 bucket counters/cursors + 257 chunk prefixes
-    const size_t o_bitmap = carve(sizeof(u32) * (ceil_div(N, 32) + 1));
+    const size_t o_bitmap = carve(sizeof(u32) * (ceil_div(N, 32) + 1) + 1024);  // + one tile of flag bytes past the end
+    const size_t o_bitmap2 = carve(sizeof(u32) * (ceil_div(N, 32) + 1) + 1024);
     const size_t o_swords = carve(sizeof(u64) * kScanWordsPerTile * ctx->scan_tiles);
     const size_t o_mstarts = carve(sizeof(u32) * (kMaxManyBlocks + 1));
     const size_t o_morigins = carve(sizeof(unsigned long long) * kMaxManyBlocks);
@@ -1414,6 +1448,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     ctx->counters = (u32*)(base + o_counters);
     ctx->scan_words = (u64*)(base + o_swords);
     ctx->bitmap = (u32*)(base + o_bitmap);
+    ctx->bitmap2 = (u32*)(base + o_bitmap2);
     ctx->bucket_hist = (u32*)(base + o_bhist);
     ctx->many_starts = (u32*)(base + o_mstarts);
     ctx->many_origins = (unsigned long long*)(base + o_morigins);

@@ -104,7 +104,7 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
     typedef PipeSmem<THREADS, ITEMS> Smem;
     typedef StatusTraits<StatusT> ST;
     constexpr int TILE = Smem::kTile;
-    static_assert(!GEN || TILE >= 4096, "the text slice of a tile must end before the text does (tiles >= 1)");
+    static_assert(!GEN || (TILE + 64 + 48 <= (int)kGenStageBytes && 2 * TILE >= (int)kGenStageBytes + 32), "the staged text slice must cover a tile and end before the text does (tiles >= 1)");
     extern __shared__ __align__(128) unsigned char smem_pipe[];
     Smem& s = *reinterpret_cast<Smem*>(smem_pipe);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -139,7 +139,7 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
             st_relaxed(tile_counter + 1 + s.next_tile, smid + 1u);
         }
         if (tid < kRadix / kScanners) {
-            constexpr int B = sizeof(StatusT) == 8 ? kScannerBatch / 2 : kScannerBatch;  // 96 registers either way
+            constexpr int B = (sizeof(StatusT) == 8 ? kScannerBatch / 2 : kScannerBatch) / (THREADS > 256 ? 2 : 1);  // 96 registers (48 in the narrower register budget of wider CTAs)
             StatusT* row = status + s.next_tile * (kRadix / kScanners) + tid;  // this digit's word of the first unresolved tile
             u32 j = 0;
             StatusT run = 0;

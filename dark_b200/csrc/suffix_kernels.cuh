@@ -538,13 +538,22 @@ __device__ __forceinline__ u64 scan_pack(u32 flag, u32 value) { return ((u64)fla
 #ifndef DARK_RERANK_CTAS
 #define DARK_RERANK_CTAS (1024 / THREADS)
 #endif
-template <int THREADS, int ITEMS, bool ROUND0, bool PAIRS>
+// MODE 0: the single-kernel form above (decoupled look-back).
+// MODE 1 + k_rerank_scan_tiles + MODE 2 (rounds >= 1): the same result without any chain between tiles.  MODE 1 reads the
+// keys once, writes the two head-flag bitmaps (one byte per thread and bitmap) and the tile's aggregate; the scan kernel
+// turns the aggregates into exclusive prefixes; MODE 2 reads the flags, ids and old ranks and applies.  Same bytes as
+// MODE 0 plus 1/4 byte per suffix.  Measured equal to MODE 0 (C3 45.1 vs 44.6 ms, C5 33.0 vs 32.9, C4 345.5 vs 345.2:
+// what bounds the re-rank of a large round is the apply phase - shared-memory partition and scattered stores - not the
+// chain, profiles/r2_rejected.md), so MODE 0 stays the default; DARK_BWT_RERANK_CHAINFREE=1 selects this form.
+template <int THREADS, int ITEMS, bool ROUND0, bool PAIRS, int MODE = 0>
 __global__ void __launch_bounds__(THREADS, DARK_RERANK_CTAS)
 k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* __restrict__ ranks_in, u32 m, u32 n, int K, int kb,
          u32* __restrict__ isa, u32* __restrict__ sa, u32* __restrict__ out_ids, u32* __restrict__ out_ranks, ScanTileState ts,
          u32* __restrict__ tile_counter, u32* __restrict__ out_count, u32* __restrict__ pair_ids,
          u32* __restrict__ pair_vals, u32* __restrict__ pair_hist, int pair_shift, const u8* __restrict__ text,
-         u8* __restrict__ bwt_inline, u64* __restrict__ origin, u32 prefetch_ahead, u32 tag, long long* __restrict__ trace) {
+         u8* __restrict__ bwt_inline, u64* __restrict__ origin, u32 prefetch_ahead, u32 tag, long long* __restrict__ trace,
+         u8* __restrict__ flags_new, u8* __restrict__ flags_old) {
+    static_assert(MODE == 0 || !ROUND0, "the chain-free form serves the rounds after the initial sort");
     // trace != nullptr (tools/rerank_trace.py only): thread 0 stamps clock64() at the phase boundaries of its tile
 #define DARK_RSTAMP(i) do { if (trace && threadIdx.x == 0) trace[(size_t)s_tile * 8 + (i)] = clock64(); } while (0)
     const long long t_entry = trace ? clock64() : 0;
@@ -564,7 +573,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     __shared__ u32 s_bwarp[8], s_btotal;
     static_assert(WARPS >= kLookbackWarps, "look-back warps");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    if (tid == 0) s_tile = MODE == 0 ? atomicAdd(tile_counter, 1u) : blockIdx.x;  // no chain, no need for claim order
     if (PAIRS)
         for (int i = tid; i < 256; i += THREADS) s_bhist[i] = 0;
     __syncthreads();
@@ -572,7 +581,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     if (trace && tid == 0) trace[(size_t)tile * 8 + 0] = t_entry;
     DARK_RSTAMP(1);
     const u64 p0 = (u64)tile * TILE + (u64)tid * ITEMS;  // blocked arrangement
-    if (prefetch_ahead) {
+    if (MODE == 0 && prefetch_ahead) {
         // pull the input of the tile that will be claimed ~one wave from now into L2: a tile's lifetime is
         // load latency + look-back, and only two CTAs fit on an SM
         const u64 q0 = ((u64)tile + prefetch_ahead) * TILE;
@@ -588,7 +597,10 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     // keys[p0-1 .. p0+ITEMS], ids[p0 .. p0+ITEMS) (+ neighbours in round 0)
     u64 key[ITEMS + 2];
     u32 id[ITEMS + 2];
-    if (p0 + ITEMS <= m) {
+    if (MODE == 2) {
+#pragma unroll
+        for (int k = 0; k < ITEMS + 2; ++k) key[k] = 0;  // the flags come from the bitmaps
+    } else if (p0 + ITEMS <= m) {
         const ulonglong2* kv = reinterpret_cast<const ulonglong2*>(keys + p0);
 #pragma unroll
         for (int k = 0; k < ITEMS / 2; ++k) {
@@ -596,7 +608,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
             key[1 + 2 * k] = q.x;
             key[2 + 2 * k] = q.y;
         }
-        if (ROUND0 || !kRerankDeferLoads) {
+        if (ROUND0 || (!kRerankDeferLoads && MODE == 0)) {
             const uint4* iv = reinterpret_cast<const uint4*>(ids + p0);
 #pragma unroll
             for (int k = 0; k < ITEMS / 4; ++k) {
@@ -611,11 +623,13 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
             key[1 + k] = (p0 + k < m) ? keys[p0 + k] : 0;
-            if (ROUND0 || !kRerankDeferLoads) id[1 + k] = (p0 + k < m) ? ids[p0 + k] : 0;
+            if (ROUND0 || (!kRerankDeferLoads && MODE == 0)) id[1 + k] = (p0 + k < m) ? ids[p0 + k] : 0;
         }
     }
-    key[0] = (p0 > 0 && p0 - 1 < m) ? keys[p0 - 1] : 0;
-    key[ITEMS + 1] = (p0 + ITEMS < m) ? keys[p0 + ITEMS] : 0;
+    if (MODE != 2) {
+        key[0] = (p0 > 0 && p0 - 1 < m) ? keys[p0 - 1] : 0;
+        key[ITEMS + 1] = (p0 + ITEMS < m) ? keys[p0 + ITEMS] : 0;
+    }
     if (ROUND0) {
         id[0] = (p0 > 0 && p0 - 1 < m) ? ids[p0 - 1] : 0;
         id[ITEMS + 1] = (p0 + ITEMS < m) ? ids[p0 + ITEMS] : 0;
@@ -659,7 +673,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
             }
         }
     };
-    if (!ROUND0 && !kRerankDeferLoads) {
+    if (!ROUND0 && !kRerankDeferLoads && MODE == 0) {
         if (p0 + ITEMS <= m) {
             const uint4* rv = reinterpret_cast<const uint4*>(ranks_in + p0);
 #pragma unroll
@@ -709,6 +723,17 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
         oldh |= tail;
     }
 
+    if (MODE == 2) {  // flags of p0 .. p0+ITEMS-1 from this thread's byte, the look-ahead flag from the next byte
+        static_assert(MODE != 2 || ITEMS == 8, "one flag byte per thread");
+        const u64 b = p0 >> 3;
+        const bool ahead_in_list = p0 + ITEMS < m;
+        newh = (u32)flags_new[b] | ((ahead_in_list ? ((u32)flags_new[b + 1] & 1u) : 1u) << ITEMS);
+        oldh = (u32)flags_old[b] | ((ahead_in_list ? ((u32)flags_old[b + 1] & 1u) : 1u) << ITEMS);
+    }
+    if (MODE == 1) {
+        flags_new[p0 >> 3] = (u8)(newh & 0xFFu);
+        flags_old[p0 >> 3] = (u8)(oldh & 0xFFu);
+    }
     DARK_RSTAMP(2);
     // thread aggregate, from the flag words: latest old/new head among the valid elements, survivors
     ScanTriple agg = {0u, 0u, 0u};
@@ -729,7 +754,18 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    if (!ROUND0 && kRerankDeferLoads) load_ids_and_ranks();
+    if (MODE == 1) {  // the tile's aggregate, and done
+        if (tid == 0) {
+            ScanTriple tile_agg = {0u, 0u, 0u};
+            for (int w = 0; w < WARPS; ++w) tile_agg = scan_combine(tile_agg, s_warp[w]);
+            u64* mine = ts.words + (size_t)tile * kScanWordsPerTile;
+            mine[0] = tile_agg.gs1;
+            mine[1] = tile_agg.hs1;
+            mine[2] = tile_agg.cnt;
+        }
+        return;
+    }
+    if (!ROUND0 && (kRerankDeferLoads || MODE == 2)) load_ids_and_ranks();
     ScanTriple wprefix = {0u, 0u, 0u};
     for (int w = 0; w < warp; ++w) wprefix = scan_combine(wprefix, s_warp[w]);
     ScanTriple texcl = shfl_up_triple(incl, 1);
@@ -742,7 +778,13 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     // 32-tile window of 2,048-element tiles ran at 1.5-1.9 TB/s (profiles/r1_ncu_c5_c3_v2.md), hence
     // kLookbackWarps warps poll kLookbackWarps*32 predecessors per step and the tiles are 4,096 wide.
     DARK_RSTAMP(3);
-    if (warp < kLookbackWarps) {
+    if (MODE == 2) {
+        if (tid == 0) {  // exclusive prefix and survivor count of this tile, from k_rerank_scan_tiles
+            const u64* mine = ts.words + (size_t)tile * kScanWordsPerTile;
+            s_excl = ScanTriple{(u32)mine[0], (u32)mine[1], (u32)mine[2]};
+            s_tile_cnt = (u32)mine[3];
+        }
+    } else if (warp < kLookbackWarps) {
         ScanTriple tile_agg = {0u, 0u, 0u};
         for (int w = 0; w < WARPS; ++w) tile_agg = scan_combine(tile_agg, s_warp[w]);
         ScanTriple excl = {0u, 0u, 0u};
@@ -954,6 +996,48 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
             pair_vals[o] = s_ork[i];
         }
     }
+}
+
+// Exclusive scan of the tile aggregates of k_rerank<MODE 1>: words[t] = (latest old head + 1, latest new head + 1,
+// survivors) of tile t  ->  the same over tiles 0 .. t-1, and word 3 = the tile's own survivor count.  One CTA.
+__global__ void __launch_bounds__(1024) k_rerank_scan_tiles(u64* __restrict__ words, u32 tiles, u32* __restrict__ out_count) {
+    __shared__ ScanTriple s_warp[32];
+    __shared__ ScanTriple s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = ScanTriple{0u, 0u, 0u};
+    __syncthreads();
+    for (u32 t0 = 0; t0 < tiles; t0 += 1024) {
+        const u32 t = t0 + tid;
+        ScanTriple v = {0u, 0u, 0u};
+        if (t < tiles) {
+            const u64* w = words + (size_t)t * kScanWordsPerTile;
+            v = ScanTriple{(u32)w[0], (u32)w[1], (u32)w[2]};
+        }
+        ScanTriple incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const ScanTriple u = shfl_up_triple(incl, o);
+            if (lane >= o) incl = scan_combine(u, incl);
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        ScanTriple base = s_carry;
+        for (int w = 0; w < warp; ++w) base = scan_combine(base, s_warp[w]);
+        ScanTriple excl = shfl_up_triple(incl, 1);
+        if (lane == 0) excl = ScanTriple{0u, 0u, 0u};
+        excl = scan_combine(base, excl);
+        if (t < tiles) {
+            u64* w = words + (size_t)t * kScanWordsPerTile;
+            w[0] = excl.gs1;
+            w[1] = excl.hs1;
+            w[2] = excl.cnt;
+            w[3] = v.cnt;
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = scan_combine(base, incl);
+        __syncthreads();
+    }
+    if (tid == 0) *out_count = s_carry.cnt;
 }
 
 // ---- sparse round-0 re-rank (pruned initial sort: almost every suffix settles) -------------------------------

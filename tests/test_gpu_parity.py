@@ -166,6 +166,10 @@ FORCED_PATHS = [
     ({"DARK_BWT_SORT_VARIANT": "0"}, "mixed", 4, 700001),            # the other radix-pass tilings
     ({"DARK_BWT_SORT_VARIANT": "2"}, "mixed", 4, 700001),
     ({"DARK_BWT_SORT_VARIANT": "5"}, "dna", 1, 700001),
+    ({"DARK_BWT_RERANK_CHAINFREE": "1"}, "mixed", 4, 1300001),        # rounds >= 1 re-ranked by flags + scan + apply (no look-back chain)
+    ({"DARK_BWT_RERANK_CHAINFREE": "1"}, "rep17", 2, 800001),
+    ({"DARK_BWT_RERANK_CHAINFREE": "1", "DARK_BWT_BUCKETED": "1"}, "mixed", 6, 2100001),
+    ({"DARK_BWT_RERANK_CHAINFREE": "1", "DARK_BWT_TEXT_BUILD": "1000000"}, "text", 6, 800001),
     ({"DARK_BWT_PASS_IMPL": "0"}, "mixed", 9, 900001),               # the round-1 pass kernel (fallback of unaligned inputs / digits)
     ({"DARK_BWT_PASS_IMPL": "0"}, "dna", 7, 1000003),                # ... with its key-generating variant
     ({"DARK_BWT_PASS_IMPL": "0", "DARK_BWT_FORCE_U64_STATUS": "1"}, "rep17", 5, 600007),
