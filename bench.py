@@ -333,7 +333,7 @@ def run_native(args, rank, local_rank, world):
     # ---- C5 (the multi-block configuration): blocks mixed(1000+b), b = rank, rank+N, ..., through the pipelined batch entry
     c5 = None
     if args.workload == "c2" and (world > 1 or args.c5_blocks > 0):
-        per_rank = args.c5_blocks if args.c5_blocks > 0 else 2
+        per_rank = args.c5_blocks if args.c5_blocks > 0 else 4
         ids = [rank + i * world for i in range(per_rank)]
         texts = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in ids]
         bwts = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in ids]
@@ -396,7 +396,7 @@ def run_native(args, rank, local_rank, world):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": desc, "block_bytes": n, "blocks_per_step": world, "sharding": "independent blocks, no collective",
-                       "l2": "inputs larger than L2 (text %d MiB, working set ~%.1f GiB): no flush between steps" % (n >> 20, 46.5 * n / 2**30),
+                       "l2": "inputs larger than L2 (text %d MiB, working set ~%.1f GiB): no flush between steps" % (n >> 20, 45.0 * n / 2**30),
                        "origin": origin, "bwt_crc32": main_crc,
                        "parity": ("ok" if (fx and fx["bwt_crc32"] == main_crc and fx["origin"] == origin) else ("MISMATCH" if fx else "no fixture")),
                        "sigma": stats["sigma"], "symbols_per_key": stats["symbols_per_key"],
@@ -459,7 +459,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-workloads", action="store_true", help="skip the c3/c5 sub-records of the 1-GPU run")
-    ap.add_argument("--c5-blocks", type=int, default=0, help="C5 blocks per rank for the `c5` sub-record (default: 2 when N > 1, none at N = 1)")
+    ap.add_argument("--c5-blocks", type=int, default=0, help="C5 blocks per rank for the `c5` sub-record (default: 4 when N > 1, none at N = 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

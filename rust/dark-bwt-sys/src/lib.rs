@@ -39,8 +39,26 @@ pub struct dark_bwt_stats {
     pub reserved_: u32,
 }
 
+#[repr(C)]
+pub struct dark_bwt_dc_info {
+    pub init: [u64; 256],
+    pub mtf_symbols: [u8; 256],
+    pub num_unique: u32,
+    pub reserved_: u32,
+    pub num_items: u64,
+    pub device_ms: f32,
+    pub reserved2_: u32,
+}
+
 extern "C" {
     pub fn dark_bwt_abi_version() -> c_int;
+    pub fn dark_bwt_dc_encode(ctx: *mut dark_bwt_ctx, bwt: *const u8, n: u64, dist_out: *mut u32, item_pos: *mut u32,
+                              item_dist: *mut u32, item_sym: *mut u8, item_rank: *mut u8, info: *mut dark_bwt_dc_info) -> c_int;
+    pub fn dark_bwt_dc_encode_device(ctx: *mut dark_bwt_ctx, d_bwt: *const u8, n: u64, d_dist_out: *mut u32, d_item_pos: *mut u32,
+                                     d_item_dist: *mut u32, d_item_sym: *mut u8, d_item_rank: *mut u8, info: *mut dark_bwt_dc_info) -> c_int;
+    pub fn dark_bwt_forward_dc(ctx: *mut dark_bwt_ctx, text: *const u8, n: u64, bwt_out: *mut u8, origin_out: *mut u64,
+                               dist_out: *mut u32, item_pos: *mut u32, item_dist: *mut u32, item_sym: *mut u8, item_rank: *mut u8,
+                               info: *mut dark_bwt_dc_info, stats: *mut dark_bwt_stats) -> c_int;
     pub fn dark_bwt_create(max_n: u64, device: c_int, out: *mut *mut dark_bwt_ctx) -> c_int;
     pub fn dark_bwt_create_ex(max_n: u64, device: c_int, flags: u32, out: *mut *mut dark_bwt_ctx) -> c_int;
     pub fn dark_bwt_capacity(ctx: *const dark_bwt_ctx) -> u64;

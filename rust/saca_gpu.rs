@@ -21,7 +21,8 @@ pub struct Constructor {
     ctx: *mut sys::dark_bwt_ctx,
     n: usize,
     sa: Vec<Suffix>,   // host copy handed out by compute()
-    out: Vec<Symbol>,
+    out: Vec<Symbol>,  // the BWT bytes of the block compute() saw last (kept: the transform produces them anyway)
+    origin: usize,
 }
 
 fn check(ctx: *const sys::dark_bwt_ctx, rc: i32, what: &str) {
@@ -35,12 +36,20 @@ fn check(ctx: *const sys::dark_bwt_ctx, rc: i32, what: &str) {
 }
 
 impl Constructor {
-    /// Create a new instance for a given maximum input size
+    /// Create a new instance for a given maximum input size (on the CUDA device named by the environment variable
+    /// `DARK_BWT_DEVICE`, default 0 — the reference's signature has no room for a device argument)
     pub fn new(max_n: usize) -> Constructor {
+        let device = std::env::var("DARK_BWT_DEVICE").ok().and_then(|v| v.parse::<i32>().ok()).unwrap_or(0);
+        Constructor::with_device(max_n, device)
+    }
+
+    /// Same, on an explicit CUDA device: one `Constructor` (one context) per GPU and host thread is how independent
+    /// blocks are spread over the GPUs of a box
+    pub fn with_device(max_n: usize, device: i32) -> Constructor {
         let mut ctx = ptr::null_mut();
-        let rc = unsafe { sys::dark_bwt_create(max_n as u64, 0, &mut ctx) };
+        let rc = unsafe { sys::dark_bwt_create(max_n as u64, device, &mut ctx) };
         check(ctx, rc, "saca::Constructor::new");
-        Constructor { ctx: ctx, n: max_n, sa: Vec::new(), out: Vec::new() }
+        Constructor { ctx: ctx, n: max_n, sa: Vec::new(), out: Vec::new(), origin: 0 }
     }
 
     /// Return maximum block size
@@ -57,7 +66,14 @@ impl Constructor {
         let rc = unsafe { sys::dark_bwt_forward(self.ctx, input.as_ptr(), input.len() as u64,
             self.out.as_mut_ptr(), &mut origin, self.sa.as_mut_ptr(), ptr::null_mut()) };
         check(self.ctx, rc, "saca::Constructor::compute");
+        self.origin = origin as usize;
         &self.sa[..]
+    }
+
+    /// BWT bytes and origin of the block `compute` was last called on (what `TransformIterator::new(input, suf)`
+    /// would yield), without a second transform
+    pub fn last_bwt(&self) -> (&[Symbol], usize) {
+        (&self.out[..], self.origin)
     }
 
     /// BWT bytes and origin of a block: what `compute` + `bwt::TransformIterator` produced
@@ -82,6 +98,25 @@ impl Constructor {
             origins.as_mut_ptr(), blocks.len() as u64, ptr::null_mut()) };
         check(self.ctx, rc, "saca::Constructor::bwt_many");
         outs.into_iter().zip(origins.into_iter().map(|o| o as usize)).collect()
+    }
+
+    /// `compute` + `TransformIterator` + `bwt::dc::encode(&output, suf, &mut mtf)` (block/dc.rs:45-52) in one call: the
+    /// distance coder reads the BWT while it is still in HBM.  Returns (BWT bytes, origin, init = `get_init()`); the
+    /// distances land in the first n words of `reuse()`, exactly where the reference passes `suf` to `dc::encode`, so
+    /// `bwt::dc::EncodeIterator::new(&output, &suf[..n], init)` continues as before.  PARITY UNPINNED for the DC part:
+    /// the `compress` crate's source is not in the reference tree (see include/dark_bwt.h).
+    pub fn bwt_dc(&mut self, input: &[Symbol]) -> (Vec<Symbol>, usize, [usize; 0x100]) {
+        let n = input.len();
+        let mut out = vec![0u8; n];
+        let mut origin = 0u64;
+        let mut info: sys::dark_bwt_dc_info = unsafe { std::mem::zeroed() };
+        let dist = self.reuse().as_mut_ptr();
+        let rc = unsafe { sys::dark_bwt_forward_dc(self.ctx, input.as_ptr(), n as u64, out.as_mut_ptr(), &mut origin, dist,
+            ptr::null_mut(), ptr::null_mut(), ptr::null_mut(), ptr::null_mut(), &mut info, ptr::null_mut()) };
+        check(self.ctx, rc, "saca::Constructor::bwt_dc");
+        let mut init = [0usize; 0x100];
+        for (d, s) in init.iter_mut().zip(info.init.iter()) { *d = *s as usize; }
+        (out, origin as usize, init)
     }
 
     /// Temporarily provide the storage for outside needs
