@@ -2,21 +2,31 @@
 //
 //   * TMA bulk staging.  One elected thread brings the NEXT tile's keys and values (or, in the key-generating
 //     first pass, its slice of the text) from HBM into a shared-memory stage with cp.async.bulk (SASS: UBLKCP),
-//     completion signalled on an mbarrier, while the CTA ranks the current tile: no thread ever waits on a
+//     completion signalled on an mbarrier, while the CTA scatters and re-orders: no thread ever waits on a
 //     global load, and the pairs live in registers only from the stage to the re-order.
-//   * A scanner CTA instead of a look-back.  In round 1 every tile walked 10-25 predecessor status rows, three
+//   * Scanner CTAs instead of a look-back.  In round 1 every tile walked 10-25 predecessor status rows: three
 //     L2 round trips of 2-3 k cycles each on its critical path and 18 % of its instructions
-//     (profiles/r1_pass_trace_v4.md).  Here the first CTA to arrive (ticket 0 of the tile counter) does not sort:
-//     it sweeps the status rows in tile order, 96 loads in flight per digit, and turns every published digit count
-//     [1 | count] into the tile's exclusive prefix [2 | prefix].  A worker publishes its counts after ranking tile
-//     j, goes on to rank tile j+1 (tile j sits re-ordered in shared memory meanwhile), and then reads ONE word per
-//     digit - its own row, long since resolved - before it scatters tile j.
-//   * Tiles are claimed from a counter (so only running CTAs ever own a tile and the look-back cannot wait on a
-//     CTA that is not resident), two tiles ahead: the atomic's latency is never exposed after the first tile.
-//   * Leaner inner loops: predicated (branch-free) leader store, values carried in registers, no debug hooks.
+//     (profiles/r1_pass_trace_v4.md).  Here the first kScanners CTAs to arrive (tickets 0 .. kScanners-1 of the
+//     tile counter) do not sort: scanner k owns 256 / kScanners digits, sweeps their status words in tile order
+//     with three batches of 32 rows in flight per digit, and turns every published digit count [1 | count] into
+//     the tile's exclusive prefix [2 | prefix].  A worker publishes its counts after ranking tile j, goes on to
+//     load and rank tile j+1 (tile j sits re-ordered in shared memory meanwhile), and then reads ONE word per
+//     digit - its own row, resolved long before - and scatters tile j.  The worker CTA that shares an SM with a
+//     scanner retires (its scatter stores would queue ahead of the scanner's loads in the SM's memory pipeline).
+//   * Tickets.  Tiles are claimed from a counter, so only running CTAs ever own a tile and nothing can wait on a
+//     CTA that is not resident.  A ticket is taken AFTER the wait for the previous tile's prefix and used for a
+//     load that lands during the scatter and re-order: the scanners work in tile order, so every tile behind a
+//     late one waits for it, and a wait between taking a ticket and publishing its counts would feed on itself
+//     (measured: 1.16 -> 0.92 ms per 2^27-pair pass, profiles/r2_rejected.md).
+//   * Leaner inner loops: 69 instructions per 32 pairs instead of 104 (8 ballots folded by four 3-input ANDs,
+//     predicated leader store, values carried in registers, no debug hooks in release builds).
+//
+// Bound: shared-memory wavefronts.  ncu (profiles/r2_ncu_pass_tma.md): LSU data pipe 75 % busy, 4,200 wavefronts per
+// 4,096-pair tile of which half are bank conflicts of the digit-indexed accesses (per-warp counters, re-order); DRAM
+// traffic 1.003 x the algorithmic 24 B per pair; 4.0 TB/s = 0.61 of the measured HBM copy peak (round 1: 0.48-0.53).
 //
 // Same contract as k_onesweep_pass: one stable LSD pass on the byte-aligned digit at `shift`, 12 B read +
-// 12 B written per pair.  The status buffer must be zeroed for (tiles + kScannerBatch) rows.
+// 12 B written per pair.  The status buffer must be zeroed for (tiles + 3 * kScannerBatch) rows.
 // Replaces the induced-sorting sweeps of the reference (/root/reference/src/saca.rs:99-163).
 #pragma once
 
@@ -481,7 +491,8 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
             const u32 nxt = retire ? ~0u : claimed - (u32)kScanners;  // the first tickets are the scanners'
             // A worker that shares its SM with the scanner retires (its stores would queue ahead of the scanner's loads
             // in the SM's memory pipeline): the ticket it has just taken is still processed, no further one is taken.
-            if (scanner_sm != 0u) retire = true;
+            // Only in a grid with workers to spare: in a tiny grid every worker could sit beside a scanner.
+            if (scanner_sm != 0u && gridDim.x >= 64u) retire = true;
             s.next_tile = nxt;
             if (nxt < num_tiles && staged(nxt)) issue_load(nxt);
         }
