@@ -357,6 +357,9 @@ int launch_pass_tma(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout
 #define DARK_PASS_THREADS 256
 #define DARK_PASS_ITEMS 16
 #endif
+#ifndef DARK_PASS_CTAS
+#define DARK_PASS_CTAS 2
+#endif
 constexpr int kDefaultSortVariant = 1;  // 256 threads x 16 items, 3 CTAs/SM: best of the sweeps in profiles/r1_sort_variants_*.log
 
 // One onesweep pass over m pairs: buffers[cur] -> buffers[cur^1].
@@ -379,7 +382,7 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
         const bool eligible = (shift & 7) == 0 && !ev && (gen == nullptr || gen->mode == 0) &&
                               (gen != nullptr || (prev_text == nullptr && ((uintptr_t)kin & 15) == 0 && ((uintptr_t)vin & 15) == 0));
         if (impl != 0 && eligible) {
-            return launch_pass_tma<DARK_PASS_THREADS, DARK_PASS_ITEMS, 2, DARK_PASS_ILP>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, gen);
+            return launch_pass_tma<DARK_PASS_THREADS, DARK_PASS_ITEMS, DARK_PASS_CTAS, DARK_PASS_ILP>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, gen);
         }
     }
     if (gen != nullptr) return launch_pass_variant<256, 16, 3, 2>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, n_text, gen);

@@ -149,7 +149,7 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
             st_relaxed(tile_counter + 1 + s.next_tile, smid + 1u);
         }
         if (tid < kRadix / kScanners) {
-            constexpr int B = (sizeof(StatusT) == 8 ? kScannerBatch / 2 : kScannerBatch) / (THREADS > 256 ? 2 : 1);  // 96 registers (48 in the narrower register budget of wider CTAs)
+            constexpr int B = (sizeof(StatusT) == 8 ? kScannerBatch / 2 : kScannerBatch) / (THREADS * MINBLOCKS > 512 ? 2 : 1);  // 96 registers (48 in the narrower register budget of wider CTAs)
             StatusT* row = status + s.next_tile * (kRadix / kScanners) + tid;  // this digit's word of the first unresolved tile
             u32 j = 0;
             StatusT run = 0;
