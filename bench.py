@@ -334,7 +334,7 @@ def run_native(args, rank, local_rank, world):
     c5 = None
     if args.workload == "c2" and (world > 1 or args.c5_blocks > 0):
         per_rank = args.c5_blocks if args.c5_blocks > 0 else 4
-        ids = [rank + i * world for i in range(per_rank)]
+        ids = blocks.corpus_blocks(rank, world, per_rank)
         texts = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in ids]
         bwts = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in ids]
         for b, t in zip(ids, texts):
@@ -359,15 +359,9 @@ def run_native(args, rank, local_rank, world):
     if c5 is not None:
         c5_wall, c5_bytes = blocks.aggregate(c5["wall_ms"], c5["bytes"])
         c5_dev, _ = blocks.aggregate(c5["device_ms"], 0)
-        allrec = [None] * world
-        if world > 1:
-            dist.all_gather_object(allrec, c5["local"])
-        else:
-            allrec = [c5["local"]]
+        flat = blocks.gather_records(c5["local"])
         if rank == 0:
-            flat = sorted(r for part in allrec for r in part)
-            import zlib
-            digest = "%08x" % (zlib.crc32(",".join(r[2] for r in flat).encode()) & 0xFFFFFFFF)
+            digest = blocks.corpus_digest(flat)
             checked = {}
             for b, o, crc in flat:
                 g = gold.get("mixed:%d:%d" % (1000 + b, n))

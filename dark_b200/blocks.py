@@ -37,3 +37,26 @@ def aggregate(ms_local, units_local, group=None):
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     dist.all_reduce(u, op=dist.ReduceOp.SUM, group=group)
     return float(t.item()), int(u.item())
+
+
+def corpus_blocks(rank, world_size, per_rank):
+    """Block numbers rank `rank` takes when every rank transforms `per_rank` blocks of the corpus: b = rank + i * world_size
+    (the same round-robin as `shard` over per_rank * world_size blocks)."""
+    return shard(per_rank * world_size, rank, world_size)
+
+
+def gather_records(local_records, group=None):
+    """All ranks' per-block records [(block, origin, crc32 hex), ...] merged and ordered by block number (on every rank).
+    The only exchange of the multi-block path, and it is off the data path: a few bytes per block, after the timing."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return sorted(list(r) for r in local_records)
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, [list(r) for r in local_records], group=group)
+    return sorted(r for part in parts for r in part)
+
+
+def corpus_digest(records):
+    """CRC-32 over the per-block BWT CRCs in block order: equal for equal block sets however they were sharded."""
+    import zlib
+    return "%08x" % (zlib.crc32(",".join(r[2] for r in sorted(records)).encode()) & 0xFFFFFFFF)

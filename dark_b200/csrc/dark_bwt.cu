@@ -187,6 +187,11 @@ struct dark_bwt_ctx {
     DeviceScalars* scalars = nullptr;
     void* sort_status = nullptr;
     size_t sort_status_bytes = 0;
+    // Sorts of fewer than 2^30 pairs use 32-bit status words and the buffer as two halves in turn: the workers of a pass zero
+    // the rows of the OTHER half (onesweep_tma.cuh), so only what they did not cover is cleared by a memset.  Rows [lo, hi)
+    // of half h may hold stale words.
+    int status_cur = 0;
+    u32 status_dirty_lo[2] = {0u, 0u}, status_dirty_hi[2] = {0u, 0u};
     u32* counters = nullptr;
     u64* scan_words = nullptr;
     long long* pass_trace = nullptr;  // debug: per-tile phase stamps of the radix pass (dark_bwt_debug_trace)
@@ -302,6 +307,10 @@ int launch_pass_variant(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* 
     const size_t bytes = (size_t)tiles * kRadix * (wide ? sizeof(u64) : sizeof(u32));
     if (bytes > ctx->sort_status_bytes) return ctx->fail_internal("sort status buffer too small");
     CK(cudaMemsetAsync(ctx->sort_status, 0, bytes, ctx->stream));
+    {  // this kernel uses the buffer from its start: both halves of the TMA pass' bookkeeping are stale now
+        const u32 half_rows = (u32)(ctx->sort_status_bytes / 2 / (kRadix * sizeof(u32)));
+        for (int h = 0; h < 2; ++h) ctx->status_dirty_lo[h] = 0u, ctx->status_dirty_hi[h] = half_rows;
+    }
     const bool aligned = (shift & 7) == 0;  // always true for the suffix sorter; the public sort may differ
 #define LP(ST, AL) launch_pass_kernel<THREADS, ITEMS, MINBLOCKS, ILP, ST, AL>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, tiles, prev_text, n_text)
     if (gen != nullptr) {  // keys built from the text inside the pass (default tiling, byte-aligned digits only)
@@ -324,9 +333,32 @@ int launch_pass_tma(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout
                     u32* counter, bool wide, const u8* prev_text, const KeyGen* gen) {
     typedef PipeSmem<THREADS, ITEMS> Smem;
     const u32 tiles = (u32)ceil_div(m, Smem::kTile);
-    const size_t bytes = ((size_t)tiles + 3 * kScannerBatch) * kRadix * (wide ? sizeof(u64) : sizeof(u32));  // the scanner reads ahead
-    if (bytes > ctx->sort_status_bytes) return ctx->fail_internal("sort status buffer too small");
-    CK(cudaMemsetAsync(ctx->sort_status, 0, bytes, ctx->stream));
+    const u32 rows_needed = tiles + 3 * kScannerBatch;  // the scanners read ahead
+    const u32 half_rows = (u32)(ctx->sort_status_bytes / 2 / (kRadix * sizeof(u32)));
+    void* st_use = ctx->sort_status;
+    void* st_clean = nullptr;
+    if (wide) {
+        const size_t bytes = (size_t)rows_needed * kRadix * sizeof(u64);
+        if (bytes > ctx->sort_status_bytes) return ctx->fail_internal("sort status buffer too small");
+        CK(cudaMemsetAsync(ctx->sort_status, 0, bytes, ctx->stream));
+        for (int h = 0; h < 2; ++h) ctx->status_dirty_lo[h] = 0u, ctx->status_dirty_hi[h] = half_rows;
+    } else {
+        if (rows_needed > half_rows) return ctx->fail_internal("sort status buffer too small");
+        const int h = ctx->status_cur, o = h ^ 1;
+        u32* base_h = (u32*)ctx->sort_status + (size_t)h * half_rows * kRadix;
+        u32* base_o = (u32*)ctx->sort_status + (size_t)o * half_rows * kRadix;
+        if (ctx->status_dirty_hi[h] > ctx->status_dirty_lo[h]) {  // what the previous pass' workers did not zero (usually nothing)
+            CK(cudaMemsetAsync(base_h + (size_t)ctx->status_dirty_lo[h] * kRadix, 0,
+                               (size_t)(ctx->status_dirty_hi[h] - ctx->status_dirty_lo[h]) * kRadix * sizeof(u32), ctx->stream));
+        }
+        ctx->status_dirty_lo[h] = 0u;  // this pass writes rows [0, tiles) of its half ...
+        ctx->status_dirty_hi[h] = tiles;
+        if (ctx->status_dirty_hi[o] <= tiles) ctx->status_dirty_lo[o] = ctx->status_dirty_hi[o] = 0u;  // ... and zeroes rows [0, tiles) of the other
+        else ctx->status_dirty_lo[o] = std::max(ctx->status_dirty_lo[o], tiles);
+        ctx->status_cur = o;
+        st_use = base_h;
+        st_clean = base_o;
+    }
     const u32 grid = std::min<u32>(tiles + kScanners, (u32)ctx->num_sms * MINBLOCKS);  // kScanners CTAs scan, the rest sort
     const KeyGen g = gen ? *gen : KeyGen();
     const bool hi = shift >= 32;
@@ -335,7 +367,7 @@ int launch_pass_tma(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout
         auto kern = hi ? k_onesweep_tma<THREADS, ITEMS, MINBLOCKS, ILP, ST, GEN, true>                                       \
                        : k_onesweep_tma<THREADS, ITEMS, MINBLOCKS, ILP, ST, GEN, false>;                                     \
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));                      \
-        kern<<<grid, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base, (ST*)ctx->sort_status, \
+        kern<<<grid, THREADS, sizeof(Smem), ctx->stream>>>(kin, vin, kout, vout, m, shift, digit_base, (ST*)st_use, (ST*)st_clean, \
                                                            counter, g, prev_text, ctx->pass_trace);                          \
     } while (0)
     if (gen) {
@@ -1448,6 +1480,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     ctx->lut = (u8*)(base + o_lut);
     ctx->scalars = (DeviceScalars*)(base + o_scalars);
     ctx->sort_status = base + o_status;
+    for (int h = 0; h < 2; ++h) ctx->status_dirty_lo[h] = 0u, ctx->status_dirty_hi[h] = (u32)(ctx->sort_status_bytes / 2 / (kRadix * sizeof(u32)));
     ctx->counters = (u32*)(base + o_counters);
     ctx->scan_words = (u64*)(base + o_swords);
     ctx->bitmap = (u32*)(base + o_bitmap);

@@ -99,8 +99,10 @@ template <int THREADS, int ITEMS, int MINBLOCKS, int ILP, typename StatusT, bool
 __global__ void __launch_bounds__(THREADS, MINBLOCKS)
 k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
                u32* __restrict__ vals_out, const u32 m, const int shift, const u32* __restrict__ digit_base,
-               StatusT* __restrict__ status, u32* __restrict__ tile_counter, const KeyGen gen,
+               StatusT* __restrict__ status, StatusT* __restrict__ status_clean, u32* __restrict__ tile_counter, const KeyGen gen,
                const u8* __restrict__ prev_text, long long* __restrict__ trace) {
+    // status_clean (nullable): the status buffer the NEXT pass will use.  Every worker zeroes the row of each tile it
+    // processes there, so the host need not launch a memset between passes (64 MB per 2^28 pairs and a launch gap each).
     // tuning builds only (-DDARK_TUNE_TRACE, tools/pass_trace2.py): thread 0 stamps clock64() at the phase boundaries
 #ifdef DARK_TUNE_TRACE
 #define TMA_STAMP(t, i) do { if (trace && threadIdx.x == 0) trace[(size_t)(t) * 12 + (i)] = clock64(); } while (0)
@@ -412,6 +414,7 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
     for (;;) {
         const u32 nvalid = (u32)min((u64)TILE, (u64)m - (u64)tile * TILE);
         const bool full = nvalid == (u32)TILE;
+        if (status_clean != nullptr && digit_thread) status_clean[(size_t)tile * kRadix + tid] = 0;
         TMA_STAMP(tile, 0);
         if (full) {
             load_tile(BoolC<true>(), nvalid);
@@ -462,7 +465,10 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
             for (int w = 0; w < Smem::kWarps; ++w) s.warp_hist[w][tid] += dstart;
             if (have_prev) {
 #ifndef DARK_TUNE_NO_WAIT
-                while ((u32)(my_row >> ST::kShift) != 2u) my_row = ld_relaxed(status + (size_t)prev_tile * kRadix + tid);
+                while ((u32)(my_row >> ST::kShift) != 2u) {
+                    __nanosleep(32);  // the scanner is behind: do not hammer L2 with 256 polls per CTA
+                    my_row = ld_relaxed(status + (size_t)prev_tile * kRadix + tid);
+                }
 #endif
                 s.global_off[tid] = digit_base[tid] + (u32)(my_row & ST::kMask) - prev_dstart;
 #ifdef DARK_TUNE_TRACE_FINE

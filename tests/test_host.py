@@ -64,7 +64,10 @@ def _gloo_worker(rank, world, port, q):
     for b in mine:
         digest[b] = (b * 2654435761) % 1000003
     dist.all_reduce(digest)
-    q.put((rank, total_ms, total_blocks, digest.tolist()))
+    # the multi-block bench record: every rank's (block, origin, crc) rows merged in block order, one digest for the set
+    ids = blocks.corpus_blocks(rank, world, 3)
+    recs = blocks.gather_records([(b, 1000 + b, "%08x" % (b * 40503 + 7)) for b in ids])
+    q.put((rank, total_ms, total_blocks, digest.tolist(), recs, blocks.corpus_digest(recs)))
     dist.destroy_process_group()
 
 
@@ -81,10 +84,15 @@ def test_two_rank_aggregation_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     expect = [(b * 2654435761) % 1000003 for b in range(9)]
-    for rank, total_ms, total_blocks, digest in res:
+    from dark_b200 import blocks
+    one_rank = [[b, 1000 + b, "%08x" % (b * 40503 + 7)] for b in range(6)]
+    for rank, total_ms, total_blocks, digest, recs, cdig in res:
         assert total_blocks == 9
         assert total_ms == max(10.0 * 5 + 0, 10.0 * 4 + 1)
         assert digest == expect
+        assert recs == one_rank                                  # 2 ranks x 3 blocks = blocks 0..5, each exactly once
+        assert cdig == blocks.corpus_digest(one_rank)            # the digest does not depend on the sharding
+    assert blocks.corpus_blocks(1, 4, 2) == [1, 5] and blocks.gather_records([(3, 1, "aa"), (1, 2, "bb")]) == [[1, 2, "bb"], [3, 1, "aa"]]
 
 
 def test_bench_reference_arm_prints_contract_line():
