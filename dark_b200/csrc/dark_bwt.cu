@@ -1246,7 +1246,13 @@ int dc_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, DcBuffers* io, dark_b
     const u32 n = (u32)n64;
     CK(cudaSetDevice(ctx->device));
     const u32 nblocks = (u32)ceil_div(n, kDcBlock);
-    u32* tab = ctx->ranks;  // nblocks x 256 words = n/4 bytes
+    // last-occurrence tables: (nblocks + ngroups) x 256 words = n/4 + n/1024 bytes (+ 2 KB): inside the 4n-byte rank buffer for
+    // all but tiny blocks, which borrow the sort's status buffer (>= 256 KB)
+    u32* tab = ctx->ranks;
+    if (n <= 65536u) {
+        tab = (u32*)ctx->sort_status;
+        for (int h = 0; h < 2; ++h) ctx->status_dirty_lo[h] = 0u, ctx->status_dirty_hi[h] = (u32)(ctx->sort_status_bytes / 2 / (kRadix * sizeof(u32)));
+    }
     u32* run_counts = ctx->ranks_alt;
     u32* first = ctx->bucket_hist;
     u32* final_last = ctx->bucket_hist + 256;
@@ -1255,7 +1261,7 @@ int dc_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, DcBuffers* io, dark_b
     if (!io->item_dist) io->item_dist = ctx->sa;
     u32* run_start = ctx->ids[0];
     if (!io->item_sym) io->item_sym = (u8*)ctx->ids[1];
-    if (!io->item_rank) io->item_rank = (u8*)ctx->ids[1] + align_up((size_t)n, 256);
+    if (!io->item_rank) io->item_rank = (u8*)ctx->ids[1] + (size_t)n;
     unsigned long long* total_runs = (unsigned long long*)((char*)ctx->dc_info + align_up(sizeof(DcInfoDev), 8));
     cudaEvent_t ea = ctx->events[kMaxEvents - 1], eb = ctx->events[kMaxEvents - 2];
     CK(cudaEventRecord(ea, ctx->stream));
@@ -1263,11 +1269,18 @@ int dc_device(dark_bwt_ctx* ctx, const u8* d_bwt, u64 n64, DcBuffers* io, dark_b
     CK(cudaMemsetAsync(total_runs, 0, sizeof(unsigned long long), ctx->stream));
     k_dc_tables<<<nblocks, 256, 0, ctx->stream>>>(d_bwt, n, tab, first, run_counts, io->dist, total_runs);
     LAUNCHED();
-    k_dc_scan<<<1, 256, 0, ctx->stream>>>(tab, nblocks, final_last);
+    const u32 ngroups = (u32)ceil_div(nblocks, kDcGroup);
+    u32* group_last = tab + (size_t)nblocks * 256;  // ngroups x 256 words behind the table (n/4 + n/1024 bytes of the 4n)
+    k_dc_scan_groups<<<ngroups, 256, 0, ctx->stream>>>(tab, nblocks, group_last);
+    LAUNCHED();
+    k_dc_scan_carry<<<1, 256, 0, ctx->stream>>>(group_last, ngroups, final_last);
     LAUNCHED();
     k_sparse_scan<<<1, 1024, 0, ctx->stream>>>(run_counts, nblocks);  // in place: exclusive run offsets
     LAUNCHED();
-    k_dc_ranks<<<(u32)ceil_div(nblocks, 8), 256, 0, ctx->stream>>>(d_bwt, n, tab, run_counts, nblocks, io->dist, run_start, io->item_sym, io->item_rank);
+    u32* alpha = ctx->bucket_hist + 512;  // 513 words: dense codes of the symbols that occur
+    k_dc_alphabet<<<1, 256, 0, ctx->stream>>>(first, alpha);
+    LAUNCHED();
+    k_dc_ranks<<<(u32)ceil_div(nblocks, 8), 256, 0, ctx->stream>>>(d_bwt, n, tab, group_last, run_counts, nblocks, alpha, io->dist, run_start, io->item_sym, io->item_rank);
     LAUNCHED();
     k_dc_final<<<1, 256, 0, ctx->stream>>>(n, final_last, first, io->dist, total_runs, ctx->dc_info);
     LAUNCHED();
@@ -1443,7 +1456,7 @@ int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx*
     const size_t o_scalars = carve(sizeof(DeviceScalars));
     const size_t o_status = carve(ctx->sort_status_bytes);
     const size_t o_counters = carve(sizeof(u32) * kMaxCounters);
-    const size_t o_bhist = carve(sizeof(u32) * 1024);  // 256 bucket counters/cursors + 257 chunk prefixes
+    const size_t o_bhist = carve(sizeof(u32) * 1280);  // 256 bucket counters/cursors + 257 chunk prefixes; DC: first/last occurrences + dense alphabet
     const size_t o_bitmap = carve(sizeof(u32) * (ceil_div(N, 32) + 1) + 1024);  // + one tile of flag bytes past the end
     const size_t o_bitmap2 = carve(sizeof(u32) * (ceil_div(N, 32) + 1) + 1024);
     const size_t o_swords = carve(sizeof(u64) * kScanWordsPerTile * ctx->scan_tiles);

@@ -17,9 +17,10 @@
 // symbols whose last occurrence before i' is later than that of s.
 //   k_dc_tables   per 4,096-byte block: last occurrence of every symbol inside the block, first occurrences, run count;
 //                 fills distances[] with the filler                                   (n read, 4n written)
-//   k_dc_scan     per symbol: running "last occurrence before block b" over the blocks  (n/16 bytes)
-//   k_dc_ranks    one warp per block walks its run starts with the 256-entry table in shared memory (8 entries per
-//                 lane, one compare each, one warp reduction): rank, distance of the previous run of s, run record
+//   k_dc_scan_*   per symbol: running "last occurrence before block b" over the blocks, in two levels  (n/16 bytes)
+//   k_dc_ranks    one warp per block walks its run starts with the last-occurrence table in registers (alphabets of up to
+//                 32 symbols: one shuffle, one compare, one ballot per run) or in shared memory (8 entries per lane, one
+//                 compare each, one warp reduction): rank, distance of the previous run of s, run record
 //   k_dc_final    last runs and the final MTF order;   k_dc_stream   run ends + their distances, compacted
 #pragma once
 
@@ -82,13 +83,20 @@ k_dc_tables(const u8* __restrict__ bwt, u32 n, u32* __restrict__ tab, u32* __res
     }
 }
 
-// tab[b][c] (last occurrence + 1 of c inside block b, 0 = none)  ->  last occurrence + 1 of c BEFORE block b;
-// final_last[c] = over the whole input.
-__global__ void __launch_bounds__(256) k_dc_scan(u32* __restrict__ tab, u32 nblocks, u32* __restrict__ final_last) {
+// tab[b][c] (last occurrence + 1 of c inside block b, 0 = none)  ->  last occurrence + 1 of c BEFORE block b, in two
+// levels so that no thread walks more than kDcGroup + ngroups rows (one CTA walking all n / 4096 rows took 5 ms of a
+// 16 ms stage on a 256 MiB block):
+//   k_dc_scan_groups  CTA g, thread c: running last occurrence over the kDcGroup blocks of group g, starting from "none";
+//                     group_last[g][c] = the group's own last occurrence
+//   k_dc_scan_carry   one CTA: group_last[g][c] -> last occurrence before group g; final_last[c] = over the whole input
+// A reader takes tab[b][c], or the carry of b's group where the group has not seen c before b.
+constexpr int kDcGroup = 256;
+__global__ void __launch_bounds__(256) k_dc_scan_groups(u32* __restrict__ tab, u32 nblocks, u32* __restrict__ group_last) {
     const int c = threadIdx.x;
+    const u32 b0 = blockIdx.x * kDcGroup, b1 = min(nblocks, b0 + kDcGroup);
     u32 run = 0;
-    u32 b = 0;
-    for (; b + 8 <= nblocks; b += 8) {
+    u32 b = b0;
+    for (; b + 8 <= b1; b += 8) {
         u32 t[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) t[k] = tab[(size_t)(b + k) * 256 + c];
@@ -98,25 +106,73 @@ __global__ void __launch_bounds__(256) k_dc_scan(u32* __restrict__ tab, u32 nblo
             if (t[k]) run = t[k];
         }
     }
-    for (; b < nblocks; ++b) {
+    for (; b < b1; ++b) {
         const u32 t = tab[(size_t)b * 256 + c];
         tab[(size_t)b * 256 + c] = run;
+        if (t) run = t;
+    }
+    group_last[(size_t)blockIdx.x * 256 + c] = run;
+}
+__global__ void __launch_bounds__(256) k_dc_scan_carry(u32* __restrict__ group_last, u32 ngroups, u32* __restrict__ final_last) {
+    const int c = threadIdx.x;
+    u32 run = 0;
+    for (u32 g = 0; g < ngroups; ++g) {
+        const u32 t = group_last[(size_t)g * 256 + c];
+        group_last[(size_t)g * 256 + c] = run;
         if (t) run = t;
     }
     final_last[c] = run;
 }
 
+// Dense codes of the symbols that occur (first[c] != ~0): alpha[0..255] = byte -> code, alpha[256..511] = code -> byte,
+// alpha[512] = sigma.  One CTA of 256 threads.
+__global__ void __launch_bounds__(256) k_dc_alphabet(const u32* __restrict__ first, u32* __restrict__ alpha) {
+    __shared__ u32 s_warp[8];
+    const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
+    const bool present = first[c] != 0xFFFFFFFFu;
+    const u32 bal = __ballot_sync(0xffffffffu, present);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    u32 base = 0;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    const u32 code = base + __popc(bal & ((1u << lane) - 1u));
+    alpha[c] = present ? code : 0xFFu;
+    if (present) alpha[256 + code] = (u32)c;
+    if (c == 255) alpha[512] = base + __popc(bal);
+}
+
 // One warp per block.  run_offsets = exclusive scan of the blocks' run counts.
+// Alphabets of up to 32 symbols (DNA, most text) keep the table in registers, one symbol per lane: the rank of a run start
+// is one shuffle, one compare and one ballot.  Larger alphabets keep 256 entries in shared memory, 8 per lane.
 __global__ void __launch_bounds__(256)
-k_dc_ranks(const u8* __restrict__ bwt, u32 n, const u32* __restrict__ tab, const u32* __restrict__ run_offsets, u32 nblocks,
-           u32* __restrict__ dist, u32* __restrict__ run_start, u8* __restrict__ run_sym, u8* __restrict__ run_rank) {
+k_dc_ranks(const u8* __restrict__ bwt, u32 n, const u32* __restrict__ tab, const u32* __restrict__ group_carry,
+           const u32* __restrict__ run_offsets, u32 nblocks, const u32* __restrict__ alpha, u32* __restrict__ dist, u32* __restrict__ run_start, u8* __restrict__ run_sym,
+           u8* __restrict__ run_rank) {
     __shared__ u32 s_tab[8][256];
+    __shared__ u8 s_dense[256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    s_dense[threadIdx.x] = (u8)alpha[threadIdx.x];
+    const u32 sigma = alpha[512];
+    __syncthreads();
     const u32 block = blockIdx.x * 8 + warp;
     if (block >= nblocks) return;
+    const bool small = sigma <= 32u;
     u32* last = s_tab[warp];
+    u32 lastreg = 0;  // small alphabets: last occurrence + 1 of the symbol with dense code `lane`
+    const u32* carry_row = group_carry + (size_t)(block / kDcGroup) * 256;  // where the block's group had not met the symbol yet
+    if (small) {
+        if ((u32)lane < sigma) {
+            const u32 c = alpha[256 + lane];
+            const u32 t = tab[(size_t)block * 256 + c];
+            lastreg = t ? t : carry_row[c];
+        }
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) last[lane + 32 * k] = tab[(size_t)block * 256 + lane + 32 * k];
+        for (int k = 0; k < 8; ++k) {
+            const u32 t = tab[(size_t)block * 256 + lane + 32 * k];
+            last[lane + 32 * k] = t ? t : carry_row[lane + 32 * k];
+        }
+    }
     __syncwarp();
     u32 run_idx = run_offsets[block];
     const u64 block_base = (u64)block * kDcBlock;
@@ -130,27 +186,44 @@ k_dc_ranks(const u8* __restrict__ bwt, u32 n, const u32* __restrict__ tab, const
         u32 prevb = __shfl_up_sync(0xffffffffu, byte, 1);
         if (lane == 0) prevb = carry;
         u32 mask = __ballot_sync(0xffffffffu, valid && byte != prevb);
+        // run records of this chunk are written together: lane q keeps the q-th run start of the chunk
+        const u32 nruns = __popc(mask);
+        u32 rec_start = 0, rec_sym = 0, rec_rank = 0;
+        u32 q = 0;
         while (mask) {
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
             const u32 s = __shfl_sync(0xffffffffu, byte, j), ps = __shfl_sync(0xffffffffu, prevb, j);
             const u32 i = (u32)(pos0 + j);
-            if (lane == 0 && ps < 0x100u) last[ps] = i;  // the run before this one ended at i-1 (stored +1)
-            __syncwarp();
-            const u32 old = last[s];  // end + 1 of the previous run of s (0: this is its first)
-            u32 cnt = 0;
+            u32 old, rank;
+            if (small) {
+                if (ps < 0x100u && (u32)lane == (u32)s_dense[ps]) lastreg = i;  // the run before this one ended at i-1 (stored +1)
+                old = __shfl_sync(0xffffffffu, lastreg, (int)s_dense[s]);
+                rank = __popc(__ballot_sync(0xffffffffu, lastreg > old));
+            } else {
+                if (lane == 0 && ps < 0x100u) last[ps] = i;
+                __syncwarp();
+                old = last[s];  // end + 1 of the previous run of s (0: this is its first)
+                u32 cnt = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) cnt += last[lane + 32 * k] > old ? 1u : 0u;
-            const u32 rank = __reduce_add_sync(0xffffffffu, cnt);
-            if (lane == 0) {
-                if (old) dist[old - 1] = i - (old - 1u) - rank - 1u;
-                run_start[run_idx] = i;
-                run_sym[run_idx] = (u8)s;
-                run_rank[run_idx] = old ? (u8)rank : (u8)0;
+                for (int k = 0; k < 8; ++k) cnt += last[lane + 32 * k] > old ? 1u : 0u;
+                rank = __reduce_add_sync(0xffffffffu, cnt);
+                __syncwarp();
             }
-            ++run_idx;
-            __syncwarp();
+            if (lane == 0 && old) dist[old - 1] = i - (old - 1u) - rank - 1u;
+            if ((u32)lane == q) {
+                rec_start = i;
+                rec_sym = s;
+                rec_rank = old ? rank : 0u;
+            }
+            ++q;
         }
+        if ((u32)lane < nruns) {
+            run_start[run_idx + lane] = rec_start;
+            run_sym[run_idx + lane] = (u8)rec_sym;
+            run_rank[run_idx + lane] = (u8)rec_rank;
+        }
+        run_idx += nruns;
         carry = __shfl_sync(0xffffffffu, byte, 31);
     }
 }

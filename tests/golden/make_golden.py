@@ -8,7 +8,7 @@ SURVEY.md App. D generators.  Each record holds n, origin, CRC-32 of the text,
 of the BWT bytes and of the little-endian SA, the SA-IS recursion trace and the
 §8(d) LCP profile (m_r, B_alg).
 
-    python tests/golden/make_golden.py [small|full|c4]
+    python tests/golden/make_golden.py [small|full|c4|c5more]
 
 `small` (seconds) and `full` (C2/C3/C5-block shapes, minutes of CPU) write
 tests/golden/oracle_golden.json; `c4` (2 GiB block, ~15 min, ~25 GB RAM) adds
@@ -46,6 +46,7 @@ FULL = [
     ("mixed", 1001, 1 << 28),  # C5 block 1
 ]
 C4 = [("mixed", 4, 1 << 31)]
+C5MORE = [("mixed", 1000 + b, 1 << 28) for b in range(2, 8)]   # C5 blocks 2..7: what bench.py --gpus 2 transforms besides 0 and 1
 
 
 def key(kind, seed, n):
@@ -54,7 +55,7 @@ def key(kind, seed, n):
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "small"
-    cases = {"small": SMALL, "full": FULL, "c4": C4}[which]
+    cases = {"small": SMALL, "full": FULL, "c4": C4, "c5more": C5MORE}[which]
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
     gold = {}
     if os.path.exists(OUT):
