@@ -27,6 +27,20 @@ import torch.distributed as dist  # noqa: E402
 from dark_b200 import blocks as blk, saca, synth  # noqa: E402
 
 
+def fixture_check(flat, n):
+    """Blocks that have a committed oracle fixture (tests/golden/oracle_golden.json): origin and BWT CRC-32 must match."""
+    try:
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_golden.json")))
+    except Exception:
+        return None
+    out = {}
+    for b, origin, crc in flat:
+        g = gold.get("mixed:%d:%d" % (1000 + b, n))
+        if g:
+            out[str(b)] = "ok" if (g["origin"] == origin and g["bwt_crc32"] == "%08x" % crc) else "MISMATCH"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--blocks", type=int, default=128)
@@ -78,7 +92,7 @@ def main():
                           "n_gpus": world, "blocks": args.blocks, "total_bytes": total,
                           "device_MBps": total / 1e6 / (float(t[0]) / 1e3), "e2e_MBps": total / 1e6 / (float(t[1]) / 1e3),
                           "max_rank_device_ms": float(t[0]), "max_rank_wall_ms": float(t[1]),
-                          "digest": "%08x" % digest, "first_blocks": flat[:2]}), flush=True)
+                          "digest": "%08x" % digest, "first_blocks": flat[:8], "fixture_check": fixture_check(flat, n)}), flush=True)
     con.close()
     if world > 1:
         dist.destroy_process_group()
