@@ -93,6 +93,7 @@ struct Knobs {
     bool check_hist = false;        // DARK_BWT_CHECK_HIST=1 counts both ways and compares
     bool inline_emit = true;        // DARK_BWT_INLINE_EMIT=0
     bool sparse_rerank = true;      // DARK_BWT_SPARSE_RERANK=0
+    bool fuse_round0 = true;        // DARK_BWT_FUSE_ROUND0=0: round 0 of an unpruned large block without the fused bucket sink
     bool rerank_chainfree = false;  // DARK_BWT_RERANK_CHAINFREE=1: rounds >= 1 re-ranked by flags + scan + apply kernels (no look-back chain; measured
                                     // equal to the single kernel on C3/C5/C4: profiles/r2_rejected.md)
     int text_div = 8;               // DARK_BWT_TEXT_BUILD=<k>: text-order key build while m > n/k (0 = never, no isa[] tag)
@@ -124,6 +125,7 @@ struct Knobs {
         inline_emit = geti("DARK_BWT_INLINE_EMIT", 1) != 0;
         sparse_rerank = geti("DARK_BWT_SPARSE_RERANK", 1) != 0;
         rerank_chainfree = geti("DARK_BWT_RERANK_CHAINFREE", 0) != 0;
+        fuse_round0 = geti("DARK_BWT_FUSE_ROUND0", 1) != 0;
         text_div = geti("DARK_BWT_TEXT_BUILD", text_div);
         pairs = geti("DARK_BWT_PAIRS", 1) != 0;
         rank_search = geti("DARK_BWT_RANK_SEARCH", 1) != 0;
@@ -546,7 +548,7 @@ int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32
     kern<<<tiles, kScanThreads, smem, ctx->stream>>>(
         keys, ids, ROUND0 ? nullptr : ctx->ranks, m, n, K, kb, ctx->isa, sa, out_ids, ROUND0 ? ctx->ranks : ctx->ranks_alt, ts, counter,
         &ctx->mail_dev->count, sink.ids, sink.vals,
-        ctx->bucket_hist, sink.shift, text, bwt_inline, &ctx->mail_dev->origin, prefetch_ahead, ROUND0 ? 0u : ctx->tag,
+        ctx->bucket_hist, sink.shift, text, bwt_inline, &ctx->mail_dev->origin, prefetch_ahead, (ROUND0 && !PAIRS) ? 0u : ctx->tag,
         ROUND0 ? ctx->rerank_trace : nullptr, nullptr, nullptr);
     LAUNCHED();
     if (!ROUND0) std::swap(ctx->ranks, ctx->ranks_alt);
@@ -827,8 +829,30 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
             }
         }
     }
+    // isa[] entries of active suffixes carry bit 31 (blocks up to 2^31 bytes): the text-order key builder finds
+    // them by it.  DARK_BWT_TEXT_BUILD=0 switches tag and builder off; =<k> uses the builder while m > n/k.
+    const int text_div = kn.text_div;
+    const u32 tag = (text_div > 0 && (u64)n <= (1ull << 31)) ? 0x80000000u : 0u;
+    ctx->tag = tag;
+    // Scatters of more than n/16 ranks into an isa[] that outgrows L2 go through the bucketed path.
+    const bool bucketed = kn.bucketed >= 0 ? kn.bucketed != 0 : ((u64)n * 4 > (96ull << 20));
+    const int bshift = std::max(0, bit_length((u64)n - 1) - 8);
+    // A large block whose initial sort was not pruned is text-like: most suffixes survive round 0 and every rank is needed.
+    // Its round-0 re-rank then feeds the bucket regions of the rank scatter itself (every suffix reports its rank, settled
+    // ones their slot) instead of two partition passes over the SA and the survivor list afterwards.  DARK_BWT_FUSE_ROUND0=0
+    // keeps the separate passes.
+    const bool fused0 = !sparse_done && bucketed && first_pass == 0 && kn.fuse_round0;
+    PairSink sink0;
     if (!sparse_done) {
-        if (int rc = launch_rerank<true, false>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, Kc, drop, sa, ctx->ids[cur ^ 1], d_text, bwt_inline)) return rc;
+        if (fused0) {
+            sink0.ids = (u32*)ctx->keys[cur ^ 1];
+            sink0.vals = sink0.ids + align_up((size_t)n, 64);
+            sink0.shift = bshift;
+            CK(cudaMemsetAsync(ctx->bucket_hist, 0, sizeof(u32) * 256, ctx->stream));
+            if (int rc = launch_rerank<true, true>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, Kc, drop, sa, ctx->ids[cur ^ 1], d_text, bwt_inline, sink0)) return rc;
+        } else {
+            if (int rc = launch_rerank<true, false>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, Kc, drop, sa, ctx->ids[cur ^ 1], d_text, bwt_inline)) return rc;
+        }
         if (int rc = fetch_count(ctx, &m)) return rc;
     }
     span_end(ctx, sp);
@@ -838,18 +862,14 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     // survive; otherwise only the survivors' now, and per round the few that are actually read.
     bool isa_complete = true;
     int selective_rounds = 0;
-    // isa[] entries of active suffixes carry bit 31 (blocks up to 2^31 bytes): the text-order key builder finds
-    // them by it.  DARK_BWT_TEXT_BUILD=0 switches tag and builder off; =<k> uses the builder while m > n/k.
-    const int text_div = kn.text_div;
-    const u32 tag = (text_div > 0 && (u64)n <= (1ull << 31)) ? 0x80000000u : 0u;
-    ctx->tag = tag;
     const bool use_pairs = kn.pairs;
     bool pairs_mode = false;
     const bool use_search = kn.rank_search;
-    // Scatters of more than n/16 ranks into an isa[] that outgrows L2 go through the bucketed path.
-    const bool bucketed = kn.bucketed >= 0 ? kn.bucketed != 0 : ((u64)n * 4 > (96ull << 20));
-    const int bshift = std::max(0, bit_length((u64)n - 1) - 8);
-    if (m > 0) {
+    if (m > 0 && fused0) {  // the regions hold every suffix's rank already
+        sp = span_begin(ctx, PH_RERANK);
+        if (int rc = region_scatter(ctx, sink0.ids, sink0.vals, n, bshift)) return rc;
+        span_end(ctx, sp);
+    } else if (m > 0) {
         sp = span_begin(ctx, PH_RERANK);
         if (m > n / 16) {
             if (bucketed) {  // every suffix gets its rank: settled ones their slot, survivors their group rank

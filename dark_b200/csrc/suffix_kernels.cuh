@@ -893,7 +893,8 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
             // (SUF_INVALID for unsettled ones) so that the later fill can tell which slots are final.
             // isa[] entries of suffixes that stay active carry `tag` (k_build_keys_text finds them by it); a
             // suffix that settles with its rank unchanged is therefore rewritten too, to drop the tag
-            const bool changed = r_new != r_old || (tag != 0 && single);
+            // (round 0 with the bucket sink: every suffix reports its rank - its slot if settled - since isa[] is still empty)
+            const bool changed = ROUND0 || r_new != r_old || (tag != 0 && single);
             const u32 r_tagged = r_new | (single ? 0u : tag);
             if (PAIRS) {
                 if (changed) {

@@ -170,6 +170,8 @@ FORCED_PATHS = [
     ({"DARK_BWT_RERANK_CHAINFREE": "1"}, "rep17", 2, 800001),
     ({"DARK_BWT_RERANK_CHAINFREE": "1", "DARK_BWT_BUCKETED": "1"}, "mixed", 6, 2100001),
     ({"DARK_BWT_RERANK_CHAINFREE": "1", "DARK_BWT_TEXT_BUILD": "1000000"}, "text", 6, 800001),
+    ({"DARK_BWT_FUSE_ROUND0": "0", "DARK_BWT_BUCKETED": "1"}, "mixed", 4, 3300001),   # round 0 followed by separate partition passes
+    ({"DARK_BWT_FUSE_ROUND0": "0", "DARK_BWT_BUCKETED": "1"}, "text", 3, 2500000),
     ({"DARK_BWT_PASS_IMPL": "0"}, "mixed", 9, 900001),               # the round-1 pass kernel (fallback of unaligned inputs / digits)
     ({"DARK_BWT_PASS_IMPL": "0"}, "dna", 7, 1000003),                # ... with its key-generating variant
     ({"DARK_BWT_PASS_IMPL": "0", "DARK_BWT_FORCE_U64_STATUS": "1"}, "rep17", 5, 600007),
