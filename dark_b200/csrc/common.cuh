@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace dark {
 
@@ -16,6 +17,21 @@ constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;  // 64-bit keys, 8-bit digits
 
 __host__ __device__ inline u64 ceil_div(u64 a, u64 b) { return (a + b - 1) / b; }
+
+// Checked build (make -C dark_b200/csrc checked; tests run it through DARK_BWT_LIB): bounds assertions on the scattered
+// stores and table indices of the kernels.  compute-sanitizer is closed on the GPU pool this was developed on, so this is
+// the memory-safety net besides the parity tests; a violation prints its place and traps (the CUDA context dies loudly).
+#ifdef DARK_BWT_CHECKED
+#define DARK_ASSERT(cond)                                                                                     \
+    do {                                                                                                      \
+        if (!(cond)) {                                                                                        \
+            printf("DARK_ASSERT failed: %s at %s:%d (block %u thread %u)\n", #cond, __FILE__, __LINE__, blockIdx.x, threadIdx.x); \
+            __trap();                                                                                         \
+        }                                                                                                     \
+    } while (0)
+#else
+#define DARK_ASSERT(cond) do { } while (0)
+#endif
 
 // ---- memory-model helpers -------------------------------------------------------------------
 // Tile-status words of the decoupled look-back scans are written by one CTA and polled by

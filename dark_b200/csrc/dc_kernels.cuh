@@ -210,6 +210,7 @@ k_dc_ranks(const u8* __restrict__ bwt, u32 n, const u32* __restrict__ tab, const
                 rank = __reduce_add_sync(0xffffffffu, cnt);
                 __syncwarp();
             }
+            DARK_ASSERT(old <= i && (old == 0 || i >= old + rank));
             if (lane == 0 && old) dist[old - 1] = i - (old - 1u) - rank - 1u;
             if ((u32)lane == q) {
                 rec_start = i;
@@ -218,6 +219,7 @@ k_dc_ranks(const u8* __restrict__ bwt, u32 n, const u32* __restrict__ tab, const
             }
             ++q;
         }
+        DARK_ASSERT((u64)run_idx + nruns <= (u64)n);
         if ((u32)lane < nruns) {
             run_start[run_idx + lane] = rec_start;
             run_sym[run_idx + lane] = (u8)rec_sym;

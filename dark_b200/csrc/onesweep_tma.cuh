@@ -183,6 +183,7 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
                 for (int i = 0; i < B; ++i) {
                     ok = ok && (u32)(v[i] >> ST::kShift) == 1u;
                     if (ok) {
+                        DARK_ASSERT(j + i < num_tiles);
                         st_relaxed(row + (size_t)i * kRadix, ((StatusT)2 << ST::kShift) | (run & ST::kMask));
                         run += v[i];
                         done = i + 1;
@@ -249,6 +250,7 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
             if (FULL || p < nvalid) {
                 const u64 kk = s.keys[p];
                 const u32 idx = s.global_off[digit(kk)] + p;
+                DARK_ASSERT(idx < m);
 #ifdef DARK_TUNE_NO_STORES
                 if (idx == 0xFFFFFFF3u)
 #endif
@@ -401,6 +403,7 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
         for (int k = 0; k < ITEMS; ++k) {
             if (FULL || (local0 + k * 32) < nvalid) {
                 const u32 pos = whist[digit(key[k])] + ((rank2[k / 2] >> (16 * (k & 1))) & 0xFFFFu);
+                DARK_ASSERT(pos < nvalid);
                 s.keys[pos] = key[k];
                 s.vals[pos] = val[k];
             }
@@ -442,6 +445,7 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
                 run += c;
             }
             count = run;
+            DARK_ASSERT(tile < num_tiles && count <= nvalid);
             st_relaxed(status + (size_t)tile * kRadix + tid, ((StatusT)1 << ST::kShift) | (StatusT)count);
         }
 #ifdef DARK_TUNE_TRACE_FINE

@@ -903,6 +903,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
                 }
                 v_pval[k] = r_tagged;
             } else if (!ROUND0 && changed) {
+                DARK_ASSERT(sid < n);
                 isa[sid] = r_tagged;
             }
             if (ROUND0 && single) v_sa[k] = sid;
@@ -918,6 +919,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
                 }
             }
             if (single) {
+                DARK_ASSERT(r_new < n && sid < n);
                 if (!ROUND0) sa[r_new] = sid;
             } else {
                 const u32 lq = run.cnt - tile_cnt0;  // position among this tile's survivors
@@ -1312,6 +1314,7 @@ k_scatter_regions(const u32* __restrict__ ids, const u32* __restrict__ vals, con
             uint4 i4, v4;
             asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(i4.x), "=r"(i4.y), "=r"(i4.z), "=r"(i4.w) : "l"(ids + base + q));
             asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w) : "l"(vals + base + q));
+            DARK_ASSERT((i4.x >> shift) == b && (i4.y >> shift) == b && (i4.z >> shift) == b && (i4.w >> shift) == b);
             isa[i4.x] = v4.x;
             isa[i4.y] = v4.y;
             isa[i4.z] = v4.z;

@@ -477,7 +477,7 @@ def test_cpp_mirror_runs_the_reference_known_answers(torch, tmp_path):
     exe = tmp_path / "saca_cpp_demo"
     libdir = os.path.dirname(_ffi.lib_path())
     subprocess.check_call(["g++", "-std=c++17", "-I", root, os.path.join(root, "examples", "saca_cpp_demo.cpp"), "-L", libdir,
-                           "-ldark_bwt", f"-Wl,-rpath,{libdir}", "-o", str(exe)])
+                           "-l:" + os.path.basename(_ffi.lib_path()), f"-Wl,-rpath,{libdir}", "-o", str(exe)])   # whichever build DARK_BWT_LIB names
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), (out.returncode, out.stdout, out.stderr)
 
