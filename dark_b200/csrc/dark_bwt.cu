@@ -408,6 +408,7 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
     // 32-bit status words hold prefixes below 2^30; larger sorts (2 GiB blocks) use 64-bit words.
     // DARK_BWT_FORCE_U64_STATUS=1 exercises the wide path on small inputs (tests).
     const bool wide = !(m < (1u << 30)) || ctx->knobs.force_u64_status;
+    const bool wide_tma = m > (1u << 31) || ctx->knobs.force_u64_status;  // the pipelined pass keeps 31 bits of prefix in a 4-byte word
     const bool ev = ctx->knobs.sort_variant >= 0;
     const int variant = ev ? ctx->knobs.sort_variant : kDefaultSortVariant;
     {
@@ -416,7 +417,7 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
         const bool eligible = (shift & 7) == 0 && !ev && (gen == nullptr || gen->mode == 0) &&
                               (gen != nullptr || (prev_text == nullptr && ((uintptr_t)kin & 15) == 0 && ((uintptr_t)vin & 15) == 0));
         if (impl != 0 && eligible) {
-            return launch_pass_tma<DARK_PASS_THREADS, DARK_PASS_ITEMS, DARK_PASS_CTAS, DARK_PASS_ILP>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, gen);
+            return launch_pass_tma<DARK_PASS_THREADS, DARK_PASS_ITEMS, DARK_PASS_CTAS, DARK_PASS_ILP>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide_tma, prev_text, gen);
         }
     }
     if (gen != nullptr) return launch_pass_variant<256, 16, 3, 2>(ctx, kin, vin, kout, vout, m, shift, digit_base, counter, wide, prev_text, n_text, gen);

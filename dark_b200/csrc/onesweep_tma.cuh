@@ -61,6 +61,19 @@ constexpr int kScannerBatch = 32;      // status rows per scanner batch (three i
 constexpr u32 kGenStageBytes = 4288;   // text slice of a 4,096-suffix tile: 4,096 + 64 symbols of look-ahead + alignment slack
 constexpr u32 kGenWordsOff = 8192;     // byte offset of the packed code words inside stage_keys
 
+// Status word of this pass: 0 = nothing yet, [01 | count] = the tile's digit count is published, [1 | prefix] = the
+// scanner resolved the exclusive prefix.  One flag bit on a resolved word leaves 31 (63) bits for the prefix, so the
+// 4-byte word serves every m <= 2^31 (k_onesweep_pass keeps its own two-flag-bit words, radix_sort.cuh).
+template <typename T>
+struct PipeStatus {
+    static constexpr int kBits = (int)sizeof(T) * 8;
+    static constexpr int kShift = kBits - 2;
+    static constexpr T kPub = (T)1 << (kBits - 2);
+    static constexpr T kRes = (T)1 << (kBits - 1);
+    static constexpr T kPrefix = kRes - 1;
+    __device__ static __forceinline__ bool resolved(T w) { return (w >> (kBits - 1)) != 0; }
+};
+
 // Lanes (of `peers`) whose 8-bit digit equals mine: 8 ballots, each complemented on the lanes whose bit is clear (one
 // test for seven bits at once - ptxas turns the per-bit tests into R2P - one vote and a predicated NOT per bit), folded
 // with four 3-input ANDs.  match_digit_bits (radix_sort.cuh) chains eight 2-input ANDs instead.
@@ -114,7 +127,7 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
     static_assert(THREADS >= kRadix && THREADS % 32 == 0, "one thread per digit is assumed");
     static_assert(ITEMS % 2 == 0 && 32 * ITEMS < 65536, "ranks are packed two per register");
     typedef PipeSmem<THREADS, ITEMS> Smem;
-    typedef StatusTraits<StatusT> ST;
+    typedef PipeStatus<StatusT> ST;
     constexpr int TILE = Smem::kTile;
     static_assert(!GEN || (TILE + 64 + 48 <= (int)kGenStageBytes && 2 * TILE >= (int)kGenStageBytes + 32), "the staged text slice must cover a tile and end before the text does (tiles >= 1)");
     extern __shared__ __align__(128) unsigned char smem_pipe[];
@@ -169,8 +182,8 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
                     StatusT acc = run;
 #pragma unroll
                     for (int i = 0; i < B; ++i) {
-                        st_relaxed(row + (size_t)i * kRadix, ((StatusT)2 << ST::kShift) | (acc & ST::kMask));
-                        acc += v[i];
+                        st_relaxed(row + (size_t)i * kRadix, ST::kRes | (acc & ST::kPrefix));
+                        acc += v[i] - ST::kPub;
                     }
                     run = acc;
                     j += B;
@@ -184,8 +197,8 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
                     ok = ok && (u32)(v[i] >> ST::kShift) == 1u;
                     if (ok) {
                         DARK_ASSERT(j + i < num_tiles);
-                        st_relaxed(row + (size_t)i * kRadix, ((StatusT)2 << ST::kShift) | (run & ST::kMask));
-                        run += v[i];
+                        st_relaxed(row + (size_t)i * kRadix, ST::kRes | (run & ST::kPrefix));
+                        run += v[i] - ST::kPub;
                         done = i + 1;
                     }
                 }
@@ -392,7 +405,7 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
             else rank2[k / 2] = r;
             __syncwarp();
         }
-        if ((u32)(early_row >> ST::kShift) == 2u) my_row = early_row;
+        if (ST::resolved(early_row)) my_row = early_row;
     };
 
     // ---- re-order the tile by digit in shared memory; each warp then clears its own counters for the next tile (no
@@ -446,7 +459,7 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
             }
             count = run;
             DARK_ASSERT(tile < num_tiles && count <= nvalid);
-            st_relaxed(status + (size_t)tile * kRadix + tid, ((StatusT)1 << ST::kShift) | (StatusT)count);
+            st_relaxed(status + (size_t)tile * kRadix + tid, ST::kPub | (StatusT)count);
         }
 #ifdef DARK_TUNE_TRACE_FINE
         TMA_GT(tile, 1, 255);
@@ -469,12 +482,12 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
             for (int w = 0; w < Smem::kWarps; ++w) s.warp_hist[w][tid] += dstart;
             if (have_prev) {
 #ifndef DARK_TUNE_NO_WAIT
-                while ((u32)(my_row >> ST::kShift) != 2u) {
+                while (!ST::resolved(my_row)) {
                     __nanosleep(32);  // the scanner is behind: do not hammer L2 with 256 polls per CTA
                     my_row = ld_relaxed(status + (size_t)prev_tile * kRadix + tid);
                 }
 #endif
-                s.global_off[tid] = digit_base[tid] + (u32)(my_row & ST::kMask) - prev_dstart;
+                s.global_off[tid] = digit_base[tid] + (u32)(my_row & ST::kPrefix) - prev_dstart;
 #ifdef DARK_TUNE_TRACE_FINE
                 TMA_GT(prev_tile, 2, 255);
 #endif
@@ -534,9 +547,9 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
     if (digit_thread) {
 #ifndef DARK_TUNE_NO_WAIT
         do my_row = ld_relaxed(status + (size_t)prev_tile * kRadix + tid);
-        while ((u32)(my_row >> ST::kShift) != 2u);
+        while (!ST::resolved(my_row));
 #endif
-        s.global_off[tid] = digit_base[tid] + (u32)(my_row & ST::kMask) - prev_dstart;
+        s.global_off[tid] = digit_base[tid] + (u32)(my_row & ST::kPrefix) - prev_dstart;
     }
     __syncthreads();
     if (prev_nvalid == (u32)TILE) scatter(BoolC<true>(), prev_nvalid);
