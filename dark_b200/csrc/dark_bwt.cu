@@ -516,7 +516,7 @@ int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32
     const u32 tiles = (u32)ceil_div(m, kScanTile);
     if (tiles > ctx->scan_tiles) return ctx->fail_internal("scan tile state too small");
     ScanTileState ts{ctx->scan_words};
-    constexpr size_t smem = (size_t)kScanTile * 8;
+    constexpr size_t smem = kRerankSmem<kScanTile>;
     if (!ROUND0 && ctx->knobs.rerank_chainfree) {
         // rounds >= 1: flags + tile aggregates, a scan over the aggregates, apply — no chain between tiles (suffix_kernels.cuh)
         auto kflags = k_rerank<kScanThreads, kScanItems, false, false, 1>;

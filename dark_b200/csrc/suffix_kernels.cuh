@@ -13,6 +13,12 @@
 
 namespace dark {
 
+// Staging of compacted elements in shared memory.  A thread owns ITEMS = 8 consecutive elements, so the lanes of a warp
+// store at a stride of up to 8 words: eight lanes per bank.  One pad word per 32 (one 8-byte pad per 16 for 64-bit
+// elements) spreads a stride-8 warp store over all banks and leaves the lane-consecutive read-out conflict-free.
+__host__ __device__ constexpr u32 stage_pad32(u32 i) { return i + (i >> 5); }
+__host__ __device__ constexpr u32 stage_pad64(u32 i) { return i + (i >> 4); }
+
 // ---- alphabet ---------------------------------------------------------------------------------
 // Which byte values occur?  (HBM: N bytes read.)  Plain racing stores of the constant 1 are fine.
 template <int THREADS>
@@ -300,7 +306,7 @@ k_build_keys(const u32* __restrict__ ids, const u32* __restrict__ ranks, u32 m, 
 // position-wise from the old list, whose group layout the sorted list reproduces.
 // HBM: 4n read (+ the second stream, mostly L2 hits), 12 m written.  Used while m > n/8.
 template <int THREADS, int ITEMS>
-constexpr size_t kBuildTextSmem = (size_t)THREADS * ITEMS * 12 + (size_t)kMaxPasses * kRadix * 4;
+constexpr size_t kBuildTextSmem = (size_t)stage_pad64(THREADS * ITEMS) * 8 + (size_t)stage_pad32(THREADS * ITEMS) * 4 + (size_t)kMaxPasses * kRadix * 4;
 template <int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS)
 k_build_keys_text(const u32* __restrict__ isa, u32 n, u64 h, int kb, u32 tag, u64* __restrict__ keys_out, u32* __restrict__ ids_out,
@@ -311,8 +317,8 @@ k_build_keys_text(const u32* __restrict__ isa, u32 n, u64 h, int kb, u32 tag, u6
     static_assert(ITEMS % 4 == 0, "128-bit loads");
     extern __shared__ __align__(16) unsigned char smem_text_build[];  // kBuildTextSmem<THREADS, ITEMS> bytes
     u64* s_key = reinterpret_cast<u64*>(smem_text_build);
-    u32* s_id = reinterpret_cast<u32*>(s_key + TILE);
-    u32* s_hist = s_id + TILE;
+    u32* s_id = reinterpret_cast<u32*>(s_key + stage_pad64(TILE));
+    u32* s_hist = s_id + stage_pad32(TILE);
     __shared__ u32 s_warp[WARPS];
     __shared__ u32 s_excl, s_total, s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -417,8 +423,8 @@ k_build_keys_text(const u32* __restrict__ isa, u32 n, u64 h, int kb, u32 tag, u6
         for (int k = 0; k < ITEMS; ++k) {
             if ((act >> k) & 1u) {
                 const u64 key = ((u64)((r1[k] & ~tag) >> 1) << kb) | r2[k];
-                s_key[lq] = key;
-                s_id[lq] = (u32)(i0 + k);
+                s_key[stage_pad64(lq)] = key;
+                s_id[stage_pad32(lq)] = (u32)(i0 + k);
                 hist_add_key(s_hist, key, 0, num_passes);
                 ++lq;
             }
@@ -426,8 +432,8 @@ k_build_keys_text(const u32* __restrict__ isa, u32 n, u64 h, int kb, u32 tag, u6
         __syncthreads();
         const u32 total = s_total, excl = s_excl;
         for (u32 i = tid; i < total; i += THREADS) {
-            keys_out[excl + i] = s_key[i];
-            ids_out[excl + i] = s_id[i];
+            keys_out[excl + i] = s_key[stage_pad64(i)];
+            ids_out[excl + i] = s_id[stage_pad32(i)];
         }
     }
     __syncthreads();
@@ -517,6 +523,8 @@ __device__ __forceinline__ ScanTriple shfl_up_triple(ScanTriple v, int o) {
 // path (the first version published a 16-byte payload behind a flag with three __threadfence()
 // per tile and ran at 1.2 TB/s, profiles/r1_ncu_c5_c3_v2.md).  The three words of a tile may be
 // observed in different states; each quantity is therefore resolved independently.
+template <int TILE>
+constexpr size_t kRerankSmem = (size_t)stage_pad32(TILE) * 8;
 struct ScanTileState {
     u64* words;  // [tiles][4]  (gs1, hs1, cnt, pad)
 };
@@ -565,9 +573,9 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     __shared__ ScanTriple s_excl;
     __shared__ u32 s_tile;
     __shared__ u64 s_lb[2][kLookbackWarps][3];
-    extern __shared__ __align__(16) u32 smem_rerank[];  // 8 * TILE bytes (dynamic: 1,024-thread tuning builds exceed 48 KB)
+    extern __shared__ __align__(16) u32 smem_rerank[];  // kRerankSmem<TILE> bytes (dynamic: 1,024-thread tuning builds exceed 48 KB)
     u32* s_oid = smem_rerank;         // this tile's survivors, staged for coalesced stores
-    u32* s_ork = smem_rerank + TILE;
+    u32* s_ork = smem_rerank + stage_pad32(TILE);
     __shared__ u32 s_tile_cnt;
     __shared__ u32 s_bhist[PAIRS ? 256 : 1], s_bcur[PAIRS ? 256 : 1], s_goff[PAIRS ? 256 : 1];
     __shared__ u32 s_bwarp[8], s_btotal;
@@ -922,7 +930,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
                 DARK_ASSERT(r_new < n && sid < n);
                 if (!ROUND0) sa[r_new] = sid;
             } else {
-                const u32 lq = run.cnt - tile_cnt0;  // position among this tile's survivors
+                const u32 lq = stage_pad32(run.cnt - tile_cnt0);  // position among this tile's survivors
                 s_oid[lq] = sid;
                 s_ork[lq] = r_new;
                 run.cnt += 1;
@@ -955,8 +963,8 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
     {
         const u32 tile_cnt = s_tile_cnt;
         for (u32 i = tid; i < tile_cnt; i += THREADS) {
-            out_ids[tile_cnt0 + i] = s_oid[i];
-            out_ranks[tile_cnt0 + i] = s_ork[i];
+            out_ids[tile_cnt0 + i] = s_oid[stage_pad32(i)];
+            out_ranks[tile_cnt0 + i] = s_ork[stage_pad32(i)];
         }
     }
     DARK_RSTAMP(7);
