@@ -100,7 +100,7 @@ typedef struct dark_bwt_stats {
 /* Constructor::new — allocates every device buffer for blocks of up to max_n bytes on
  * CUDA device `device`: one arena of 45 * max_n bytes of HBM (41 * max_n with DARK_BWT_F_DEVICE_ONLY; 11.2 GiB for a
  * 256 MiB block, 89.8 GiB for 2 GiB).  No device memory is allocated later; the pinned staging lanes for pageable host
- * buffers (64 MB per direction) and the `reuse` scratch are allocated by the first call that needs them. */
+ * buffers (12 lanes x 2 MiB per direction) and the `reuse` scratch are allocated by the first call that needs them. */
 int dark_bwt_create(uint64_t max_n, int device, dark_bwt_ctx **out);
 int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx **out);
 
@@ -110,7 +110,7 @@ uint64_t dark_bwt_capacity(const dark_bwt_ctx *ctx);
 /* compute + TransformIterator on HOST buffers: text[0..n) -> bwt_out[0..n), *origin_out,
  * and, if sa_out is non-null, the suffix array sa_out[0..n).  Pinned (cudaHostAlloc / cudaHostRegister) buffers are
  * DMA'd directly; pageable ones (a plain Vec<u8>, malloc) of 1 MiB or more go through the context's pinned staging
- * lanes: DARK_BWT_HOST_THREADS host threads (default 8, 0 = leave it to the driver) each copy 8 MiB chunks into their
+ * lanes: DARK_BWT_HOST_THREADS host threads (default 12, at most the host's cores less two; 0 = leave it to the driver) each copy 2 MiB chunks into their
  * own pinned chunk and send them on, so the memcpy of one lane overlaps the DMA of the others.  `stats` nullable. */
 int dark_bwt_forward(dark_bwt_ctx *ctx, const uint8_t *text, uint64_t n, uint8_t *bwt_out, uint64_t *origin_out,
                      uint32_t *sa_out, dark_bwt_stats *stats);
