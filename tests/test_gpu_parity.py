@@ -216,6 +216,48 @@ def test_large_block_code_paths_forced_on_small_inputs(oracle, idx):
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
+STAGING = [
+    {},                                                                  # defaults: 12 lanes x 2 MiB
+    {"DARK_BWT_HOST_THREADS": "1", "DARK_BWT_HOST_CHUNK_MB": "1"},       # one lane, many chunks
+    {"DARK_BWT_HOST_THREADS": "16", "DARK_BWT_HOST_CHUNK_MB": "4"},      # more lanes than chunks
+    {"DARK_BWT_HOST_THREADS": "0"},                                      # staging off: the driver's own bounce buffer
+]
+
+
+@pytest.mark.parametrize("idx", range(len(STAGING)))
+def test_pageable_host_buffers_through_the_staging_lanes(oracle, idx):
+    """The reference hands over a plain Vec<u8> and collects into a fresh one (src/main.rs:95, src/block/dc.rs:45-50):
+    pageable buffers of 1 MiB or more go through the pinned staging lanes.  Ragged sizes (not a multiple of the lane
+    chunk), the SA output (4n bytes through the same lanes), the batch entry, the inverse and the DC entry give what pinned
+    buffers and the oracle give, for every lane setting."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, oracle\n"
+        "from dark_b200 import saca, synth\n"
+        "n = 5 * (1 << 20) + 12345\n"
+        "t = synth.generate('mixed', 21, n)\n"
+        "c = saca.Constructor(n)\n"
+        "b, o, s = c.bwt_and_sa(t)\n"                                   # pageable numpy buffers in and out
+        "bo, oo, so = oracle.bwt_forward(t, want_sa=True)\n"
+        "assert o == oo and np.array_equal(b, bo) and np.array_equal(s, so)\n"
+        "pt = torch.from_numpy(t).pin_memory(); pb = torch.empty(n, dtype=torch.uint8).pin_memory()\n"
+        "assert c.bwt_into(pt.data_ptr(), n, pb.data_ptr()) == oo and np.array_equal(pb.numpy(), bo)\n"   # pinned: straight DMA
+        "blocks = [t, synth.generate('dna', 22, 3 * (1 << 20) + 7), synth.generate('text', 23, 4097), t[: 2 * (1 << 20)]]\n"
+        "for blk, (bb, ob) in zip(blocks, c.bwt_blocks(blocks)):\n"      # pipelined batch entry, pageable in and out
+        "    rb, ro = oracle.bwt_forward(blk)\n"
+        "    assert ob == ro and np.array_equal(bb, rb)\n"
+        "assert np.array_equal(c.inverse(bo, oo), t)\n"                  # unpack side, pageable
+        "d = c.bwt_dc(t)\n"                                              # BWT + distance coding, 4n bytes of distances out
+        "ref = oracle.dc_encode(bo)\n"
+        "assert np.array_equal(d[0], bo) and d[1] == oo and np.array_equal(d[2]['dist'], ref[0]) and d[2]['num_unique'] == ref[3]\n"
+        "print('ok')\n")
+    env = dict(os.environ, **STAGING[idx])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
 # ---- building blocks (SURVEY §4 T1) -------------------------------------------------------------
 @pytest.mark.parametrize("m,begin,end", [(1, 0, 64), (100, 0, 64), (4096, 0, 64), (4097, 0, 64), (1000003, 0, 64),
                                          (300000, 0, 40), (300000, 16, 48), (50000, 0, 8)])
