@@ -195,7 +195,7 @@ struct dark_bwt_ctx {
     DeviceScalars* scalars = nullptr;
     void* sort_status = nullptr;
     size_t sort_status_bytes = 0;
-    // Sorts of fewer than 2^30 pairs use 32-bit status words and the buffer as two halves in turn: the workers of a pass zero
+    // Sorts of at most 2^31 pairs use 32-bit status words and the buffer as two halves in turn: the workers of a pass zero
     // the rows of the OTHER half (onesweep_tma.cuh), so only what they did not cover is cleared by a memset.  Rows [lo, hi)
     // of half h may hold stale words.
     int status_cur = 0;
@@ -411,7 +411,8 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
         u32* scanner_sm = nullptr;  // the words after the tile counter: where the scanner CTAs of onesweep_tma.cuh say which SMs they run on
         if (int rc = next_counter(ctx, &scanner_sm)) return rc;
     }
-    // 32-bit status words hold prefixes below 2^30; larger sorts (2 GiB blocks) use 64-bit words.
+    // The round-1 kernel's 32-bit status words hold prefixes below 2^30, the pipelined pass' below 2^31 (blocks up to 2 GiB);
+    // larger sorts use 64-bit words.
     // DARK_BWT_FORCE_U64_STATUS=1 exercises the wide path on small inputs (tests).
     const bool wide = !(m < (1u << 30)) || ctx->knobs.force_u64_status;
     const bool wide_tma = m > (1u << 31) || ctx->knobs.force_u64_status;  // the pipelined pass keeps 31 bits of prefix in a 4-byte word
