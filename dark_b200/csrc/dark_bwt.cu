@@ -453,13 +453,16 @@ int launch_pass(dark_bwt_ctx* ctx, const u64* kin, const u32* vin, u64* kout, u3
 // *first_pass_out = index of the lowest digit that was sorted.
 int run_sort(dark_bwt_ctx* ctx, u64* const keys[2], u32* const vals[2], int cur, u32 m, int begin_bit, int num_passes,
              int* cur_out, dark_bwt_stats* st, int round, bool prune = false, int* first_pass_out = nullptr,
-             const u8* patch_text = nullptr, bool* patched_out = nullptr, const KeyGen* gen = nullptr, bool* gen_used_out = nullptr) {
+             const u8* patch_text = nullptr, bool* patched_out = nullptr, const KeyGen* gen = nullptr, bool* gen_used_out = nullptr,
+             bool all_passes = false) {
     // Scalar results (flags, counts, origin) are written by the kernels directly into mapped pinned host
     // memory and read after a stream sync.  A cudaMemcpy D2H would queue on the copy engine behind the
     // 256 MB block transfers of the pipelined batch entry (measured: +5 ms per block).
     k_scan_hist<<<num_passes, kRadix, 0, ctx->stream>>>(ctx->hist, m, ctx->mail_dev->trivial, ctx->mail_dev->collide);
     LAUNCHED();
-    CK(sync_counted(ctx));
+    // all_passes (a round that still holds more than n/8 suffixes): their ranks span at least m slots, so at most the
+    // top digit could be constant; every pass runs and the host does not wait for the flags (one round trip less per round)
+    if (!all_passes) CK(sync_counted(ctx));
     int first = 0;
     if (prune) {
         for (int p = 0; p < num_passes; ++p)
@@ -481,7 +484,7 @@ int run_sort(dark_bwt_ctx* ctx, u64* const keys[2], u32* const vals[2], int cur,
     const u8* patch = (first >= 1) ? patch_text : nullptr;
     int sp = span_begin(ctx, gen ? PH_GENPASS : PH_PASS);
     for (int p = first; p < num_passes; ++p) {
-        if (ctx->mail->trivial[p]) continue;  // every key has the same digit: the pass is the identity
+        if (!all_passes && ctx->mail->trivial[p]) continue;  // every key has the same digit: the pass is the identity
         if (int rc = launch_pass(ctx, keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], m, begin_bit + p * kRadixBits,
                                  ctx->hist + p * kRadix, patch, m, gen))
             return rc;
@@ -1015,7 +1018,9 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         span_end(ctx, sp);
 
         sp = span_begin(ctx, PH_SORT);
-        if (int rc = run_sort(ctx, ctx->keys, ctx->ids, cur, m, 0, passes_r, &cur, st, round)) return rc;
+        if (int rc = run_sort(ctx, ctx->keys, ctx->ids, cur, m, 0, passes_r, &cur, st, round, false, nullptr, nullptr, nullptr, nullptr, nullptr,
+                              /*all_passes=*/text_built))
+            return rc;
         span_end(ctx, sp);
 
         sp = span_begin(ctx, PH_RERANK);

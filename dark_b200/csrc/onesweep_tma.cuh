@@ -8,8 +8,8 @@
 //     L2 round trips of 2-3 k cycles each on its critical path and 18 % of its instructions
 //     (profiles/r1_pass_trace_v4.md).  Here the first kScanners CTAs to arrive (tickets 0 .. kScanners-1 of the
 //     tile counter) do not sort: scanner k owns 256 / kScanners digits, sweeps their status words in tile order
-//     with three batches of 32 rows in flight per digit, and turns every published digit count [1 | count] into
-//     the tile's exclusive prefix [2 | prefix].  A worker publishes its counts after ranking tile j, goes on to
+//     with three batches of 32 rows in flight per digit, and turns every published digit count [01 | count] into
+//     the tile's exclusive prefix [1 | prefix] (PipeStatus below).  A worker publishes its counts after ranking tile j, goes on to
 //     load and rank tile j+1 (tile j sits re-ordered in shared memory meanwhile), and then reads ONE word per
 //     digit - its own row, resolved long before - and scatters tile j.  The worker CTA that shares an SM with a
 //     scanner retires (its scatter stores would queue ahead of the scanner's loads in the SM's memory pipeline).
@@ -153,8 +153,8 @@ k_onesweep_tma(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in,
     __syncthreads();
     // ticket 0 = the scanner; ticket t > 0 = tile t-1 (only running CTAs ever hold a ticket)
     if (s.next_tile < (u32)kScanners) {
-        // Thread d owns digit d.  It walks the status rows in tile order and replaces [1 | count] by
-        // [2 | exclusive prefix] (the counts are summed with their flag; the sum is masked on output).  Three batches
+        // Thread d owns digit d.  It walks the status rows in tile order and replaces [01 | count] by
+        // [1 | exclusive prefix] (each count is added less its flag bit: one three-input add).  Three batches
         // of kScannerBatch rows are in flight per digit (registers), always starting at the first unresolved row, so
         // the scanner is never more than one round trip behind the tiles and resolves 3 * kScannerBatch rows per round
         // trip when it has fallen behind.  Rows past the last tile stay zero (never published).

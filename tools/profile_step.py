@@ -25,7 +25,7 @@ for _ in range(reps):
     origin = con.bwt_device(dt.data_ptr(), n, db.data_ptr())
     st = con.stats.as_dict()
     print(json.dumps({"workload": name, "n": n, "origin": origin, **{k: st[k] for k in (
-        "sigma", "symbols_per_key", "initial_symbols", "rounds", "sort_passes", "kernel_launches", "device_ms", "init_ms", "sort_ms", "pass_ms",
+        "sigma", "symbols_per_key", "initial_symbols", "rounds", "sort_passes", "kernel_launches", "host_syncs", "device_ms", "init_ms", "sort_ms", "pass_ms",
         "keybuild_ms", "rerank_ms", "emit_ms", "active", "passes")}}))
 # the timing is only worth reading if the bytes are right: CRC-32 of the BWT against the committed oracle fixture
 gold = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_golden.json")))
