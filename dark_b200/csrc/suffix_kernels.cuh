@@ -917,7 +917,8 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
             if (ROUND0 && single) v_sa[k] = sid;
             if (bwt_inline != nullptr && single) {
                 if (ROUND0) {
-                    const u32 byte = (u32)key[k + 1] & 0xFFu;
+                    // pruned initial sort (kb >= 8): the byte rides in the low key byte; otherwise it is gathered here
+                    const u32 byte = kb >= 8 ? ((u32)key[k + 1] & 0xFFu) : (u32)__ldg(text + (sid == 0 ? n - 1 : sid - 1));
                     if (k < 4) v_b0 |= byte << (8 * k);
                     else v_b1 |= byte << (8 * (k - 4));
                     if (sid == 0) *origin = p;
