@@ -93,7 +93,7 @@ struct Knobs {
     bool check_hist = false;        // DARK_BWT_CHECK_HIST=1 counts both ways and compares
     bool inline_emit = true;        // DARK_BWT_INLINE_EMIT=0
     bool sparse_rerank = true;      // DARK_BWT_SPARSE_RERANK=0
-    int inline_gather = -1;         // DARK_BWT_INLINE_GATHER=0/1: inline emission by gathering T[id-1] in the re-rank (default: blocks over 8 emission windows)
+    int inline_gather = 0;          // DARK_BWT_INLINE_GATHER=1: unpruned blocks emit inline too, gathering T[id-1] in the re-rank
     bool fuse_round0 = true;        // DARK_BWT_FUSE_ROUND0=0: round 0 of an unpruned large block without the fused bucket sink
     bool rerank_chainfree = false;  // DARK_BWT_RERANK_CHAINFREE=1: rounds >= 1 re-ranked by flags + scan + apply kernels (no look-back chain; measured
                                     // equal to the single kernel on C3/C5/C4: profiles/r2_rejected.md)
@@ -128,7 +128,7 @@ struct Knobs {
         sparse_rerank = geti("DARK_BWT_SPARSE_RERANK", 1) != 0;
         rerank_chainfree = geti("DARK_BWT_RERANK_CHAINFREE", 0) != 0;
         fuse_round0 = geti("DARK_BWT_FUSE_ROUND0", 1) != 0;
-        inline_gather = geti("DARK_BWT_INLINE_GATHER", -1);
+        inline_gather = geti("DARK_BWT_INLINE_GATHER", 0);
         text_div = geti("DARK_BWT_TEXT_BUILD", text_div);
         pairs = geti("DARK_BWT_PAIRS", 1) != 0;
         rank_search = geti("DARK_BWT_RANK_SEARCH", 1) != 0;
@@ -786,12 +786,10 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         cur = 0;
     }
     span_end(ctx, sp);
-    // A block whose emission would need more than 8 text windows (they would outgrow L2; C4: 37 ms for the gather pass)
-    // emits inline as well: the re-rank gathers T[id-1] for every suffix as it settles.  One random 32-byte sector per
-    // suffix either way, but hidden behind kernels that do not saturate DRAM.  DARK_BWT_INLINE_GATHER=0/1 forces it.
-    if (want_inline && !emit_inline &&
-        (kn.inline_gather > 0 || (kn.inline_gather < 0 && (u64)n > 8ull * ((u64)kn.emit_window_mb << 20))))
-        emit_inline = true;
+    // DARK_BWT_INLINE_GATHER=1: an unpruned block emits inline as well, the re-rank gathering T[id-1] for every suffix as it
+    // settles.  Measured equal to the final gather pass (C4: re-rank +38 ms, emission -37 ms: one random DRAM sector per
+    // suffix wherever the read is issued, profiles/r2_rejected.md), so it stays an option.
+    if (want_inline && !emit_inline && kn.inline_gather > 0) emit_inline = true;
     u8* bwt_inline = emit_inline ? d_bwt : nullptr;
     // The sort covered the key bits above `drop`: K0 whole leading symbols are known equal inside a
     // tie group, Kc symbols were touched (a suffix shorter than Kc had padding compared).

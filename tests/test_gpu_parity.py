@@ -190,7 +190,7 @@ FORCED_PATHS = [
     ({"DARK_BWT_FUSED_INIT": "0"}, "dna", 2, 1100003),
     ({"DARK_BWT_FORCE_U64_STATUS": "1"}, "dna", 8, 600011),          # key-generating pass with 64-bit tile status                  # late rounds WITHOUT the pairs kernel
     ({"DARK_BWT_INLINE_EMIT": "0"}, "dna", 3, 1200007),              # pruned initial sort WITHOUT inline emission
-    ({"DARK_BWT_INLINE_GATHER": "1"}, "mixed", 7, 1300003),           # unpruned block emitting inline: T[id-1] gathered as suffixes settle (blocks over 512 MiB)
+    ({"DARK_BWT_INLINE_GATHER": "1"}, "mixed", 7, 1300003),           # unpruned block emitting inline: T[id-1] gathered as suffixes settle
     ({"DARK_BWT_INLINE_GATHER": "1"}, "rep17", 8, 700001),
     ({"DARK_BWT_INLINE_GATHER": "1", "DARK_BWT_TEXT_BUILD": "1000000", "DARK_BWT_BUCKETED": "1"}, "text", 9, 2200003),  # ... with the fused round-0 bucket sink
     ({"DARK_BWT_INLINE_GATHER": "1", "DARK_BWT_PAIRS": "0"}, "text", 10, 500009),
