@@ -58,6 +58,7 @@ struct Mailbox {  // pinned host memory the device results are copied into
     u64 origin;
     unsigned long long bad;
     u32 flag;  // pairs-mode detector: set when some group has three or more members
+    u32 not_pairs;  // the same answer from the check queued behind a re-rank (read with the survivor count)
 };
 
 struct DeviceScalars {  // mirrors Mailbox on the device
@@ -227,6 +228,7 @@ struct dark_bwt_ctx {
     };
     std::vector<Span> spans;
     int next_counter = 0;
+    u32* count_dev = nullptr;  // device copy of the survivor count of the last re-rank launched (nullptr: none)
     u32 tag = 0;  // bit carried by isa[] entries of active suffixes during forward_device (0: not used)
     u32 launches = 0;
     u32 syncs = 0;
@@ -550,10 +552,13 @@ int launch_rerank(dark_bwt_ctx* ctx, const u64* keys, const u32* ids, u32 m, u32
                                                            &ctx->mail_dev->origin, 0u, ctx->tag, nullptr, fnew, fold);
         LAUNCHED();
         std::swap(ctx->ranks, ctx->ranks_alt);
+        ctx->count_dev = nullptr;  // this form leaves the count in the mailbox only
         return 0;
     }
-    u32* counter = nullptr;
+    u32 *counter = nullptr, *count_copy = nullptr;  // two consecutive words: the tile counter, then the survivor count (device copy)
     if (int rc = next_counter(ctx, &counter)) return rc;
+    if (int rc = next_counter(ctx, &count_copy)) return rc;
+    ctx->count_dev = count_copy;
     CK(cudaMemsetAsync(ctx->scan_words, 0, sizeof(u64) * kScanWordsPerTile * tiles, ctx->stream));
     const u32 prefetch_ahead = ctx->knobs.rerank_prefetch >= 0 ? (u32)ctx->knobs.rerank_prefetch : 2u * (u32)ctx->num_sms;  // one wave of CTAs ahead (-2 %)
     auto kern = k_rerank<kScanThreads, kScanItems, ROUND0, PAIRS>;
@@ -597,6 +602,22 @@ int region_scatter(dark_bwt_ctx* ctx, const u32* ids, const u32* vals, u32 upper
 int fetch_count(dark_bwt_ctx* ctx, u32* out) {
     CK(sync_counted(ctx));
     *out = ctx->mail->count;
+    return 0;
+}
+
+// Queues the pairs check (suffix_kernels.cuh, k_pairs_detect) behind the re-rank that has just been launched: it reads the
+// survivor count from the device copy the re-rank leaves beside its tile counter, and its answer (ctx->mail->not_pairs) arrives with that count in the
+// round trip the round makes anyway.  `upper` bounds the count.
+int queue_pairs_check(dark_bwt_ctx* ctx, u32 upper, bool* queued) {
+    *queued = false;
+    if (ctx->count_dev == nullptr) return 0;
+    u32* seen = nullptr;
+    if (int rc = next_counter(ctx, &seen)) return rc;
+    ctx->mail->not_pairs = 0;
+    const u32 grid = (u32)std::min<u64>(std::max<u64>(ceil_div(upper, 256), 1), (u64)ctx->num_sms * 4);
+    k_pairs_detect<<<grid, 256, 0, ctx->stream>>>(ctx->ranks, 0u, ctx->count_dev, seen, &ctx->mail_dev->not_pairs);
+    LAUNCHED();
+    *queued = true;
     return 0;
 }
 
@@ -807,6 +828,7 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
     sp = span_begin(ctx, PH_RERANK);
     u32 m = 0;
     bool sparse_done = false;
+    bool pairs_checked = false;  // the pairs check of the current list was queued behind its re-rank: the answer is in the mailbox
     // Pruned initial sort with inline emission (high-entropy block: almost everything settles): the chain-free
     // sparse re-rank (suffix_kernels.cuh).  DARK_BWT_SPARSE_RERANK=0 keeps the scan-based kernel.
     if (emit_inline && first_pass >= 1 && kn.sparse_rerank) {
@@ -870,6 +892,8 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         } else {
             if (int rc = launch_rerank<true, false>(ctx, ctx->keys[cur], ctx->ids[cur], n, n, Kc, drop, sa, ctx->ids[cur ^ 1], d_text, bwt_inline)) return rc;
         }
+        if (kn.pairs)
+            if (int rc = queue_pairs_check(ctx, n, &pairs_checked)) return rc;
         if (int rc = fetch_count(ctx, &m)) return rc;
     }
     span_end(ctx, sp);
@@ -922,16 +946,22 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         // while most of the block is still active (period-17: ten rounds of giant groups).  The kernel gathers
         // from isa[], so it waits until every rank is there (few survivors after round 0: the selective rounds).
         if (use_pairs && !pairs_mode && isa_complete && (m & 1u) == 0 && (round == 1 || m <= n / 2)) {
-            ctx->mail->flag = 0;
-            u32* seen = nullptr;
-            if (int rc = next_counter(ctx, &seen)) return rc;
-            k_pairs_detect<<<(u32)ceil_div(m, 256), 256, 0, ctx->stream>>>(ctx->ranks, m, seen, &ctx->mail_dev->flag);
-            LAUNCHED();
-            CK(sync_counted(ctx));
-            if (ctx->mail->flag == 0) {
-                pairs_mode = true;
+            if (pairs_checked) {  // answered in the round trip that fetched m
+                if (ctx->mail->not_pairs == 0) pairs_mode = true;
+            } else {
+                ctx->mail->flag = 0;
+                u32* seen = nullptr;
+                if (int rc = next_counter(ctx, &seen)) return rc;
+                k_pairs_detect<<<(u32)std::min<u64>(ceil_div(m, 256), (u64)ctx->num_sms * 8), 256, 0, ctx->stream>>>(ctx->ranks, m, nullptr, seen,
+                                                                                                                    &ctx->mail_dev->flag);
+                LAUNCHED();
+                CK(sync_counted(ctx));
+                if (ctx->mail->flag == 0) {
+                    pairs_mode = true;
+                }
             }
         }
+        pairs_checked = false;
         if (pairs_mode) {
             // every group is a pair: one kernel settles or keeps each pair (suffix_kernels.cuh, "pairs mode")
             sp = span_begin(ctx, PH_RERANK);
@@ -1046,6 +1076,9 @@ int forward_device(dark_bwt_ctx* ctx, const u8* d_text, u64 n64, u8* d_bwt, u64*
         span_end(ctx, sp);
         cur ^= 1;
         const u32 m_sorted = m;
+        if (use_pairs && isa_complete && m_sorted <= n / 2) {  // the list that comes out may be all pairs: ask now, read with the count
+            if (int rc = queue_pairs_check(ctx, m_sorted, &pairs_checked)) return rc;
+        }
         if (int rc = fetch_count(ctx, &m)) return rc;
         if (text_built && ctx->mail->flag != m_sorted) return ctx->fail_internal("tagged isa[] entries disagree with the active list");
         h *= 2;

@@ -866,7 +866,10 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ ids, const u32* _
         if (warp == 0 && lane == 0) {
             s_excl = excl;
             s_tile_cnt = tile_agg.cnt;
-            if ((u64)(tile + 1) * TILE >= m) *out_count = excl.cnt + tile_agg.cnt;  // last tile: survivors in total
+            if ((u64)(tile + 1) * TILE >= m) {  // last tile: survivors in total, for the host (mapped memory) and, in
+                *out_count = excl.cnt + tile_agg.cnt;  // device memory beside the tile counter, for kernels queued behind this one
+                tile_counter[1] = excl.cnt + tile_agg.cnt;
+            }
         }
         DARK_RSTAMP(4);
     }
@@ -1759,9 +1762,19 @@ k_lcp_buckets(const u32* __restrict__ lcp, u32 n, unsigned long long* __restrict
 // the mixed 256 MiB block has nothing but pairs from round 4 on, for 8 more rounds).  Sorting a
 // group of two needs no sort: one kernel per round gathers both second ranks, settles the pair when they
 // differ and keeps it otherwise.  Replaces key build + 7 radix passes + re-rank for those rounds.
-__global__ void __launch_bounds__(256) k_pairs_detect(const u32* __restrict__ ranks, u32 m, u32* __restrict__ seen, u32* __restrict__ not_pairs) {
-    const u64 p = (u64)blockIdx.x * 256 + threadIdx.x;
-    const int big = p + 2 < m && ranks[p] == ranks[p + 2];  // a group of three or more
+// m_ptr != nullptr: the length of the list is read from device memory (the count the re-rank before this launch has just
+// written), so the check can be queued behind the re-rank and its answer read with the survivor count in ONE round trip.
+__global__ void __launch_bounds__(256) k_pairs_detect(const u32* __restrict__ ranks, u32 m, const u32* __restrict__ m_ptr,
+                                                      u32* __restrict__ seen, u32* __restrict__ not_pairs) {
+    if (m_ptr != nullptr) {  // mapped host memory: one read per CTA
+        __shared__ u32 s_m;
+        if (threadIdx.x == 0) s_m = ld_relaxed(m_ptr);
+        __syncthreads();
+        m = s_m;
+    }
+    int big = 0;
+    for (u64 p = (u64)blockIdx.x * 256 + threadIdx.x; p + 2 < m; p += (u64)gridDim.x * 256)
+        big |= ranks[p] == ranks[p + 2];  // a group of three or more
     // `not_pairs` lives in mapped host memory: exactly one thread of the grid writes it
     if (__syncthreads_or(big) && threadIdx.x == 0 && ld_relaxed(seen) == 0 && atomicExch(seen, 1u) == 0) *not_pairs = 1;
 }
