@@ -70,39 +70,92 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled in-process every 2 ms (a timed region
+    of 20 C2 steps lasts 0.2 s, less than `nvidia-smi` needs to start), `nvidia-smi -lms 20` when NVML cannot be loaded.
+    begin() / stop() bracket the timed region; only samples taken between them count."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.h = [], None, None, None   # rows: (time, sm MHz, max MHz, [reason names])
+        self.t0 = self.t1 = None
+        self.running = True
+        self.how = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.how = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.how = "nvidia-smi"
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        mx = float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM))
+        try:
+            bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        masks = [getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        return (time.perf_counter(), sm, mx, [nm for nm, m in zip(self.NAMES, masks) if bits & m])
+
+    def _poll_nvml(self):
+        while self.running:
+            try:
+                self.rows.append(self._sample_nvml())
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            r = [c.strip() for c in line.split(",")]
+            if len(r) >= 7 and r[0].replace(".", "").isdigit() and r[1].replace(".", "").isdigit():
+                self.rows.append((time.perf_counter(), float(r[0]), float(r[1]),
+                                  [nm for k, nm in enumerate(self.NAMES) if r[3 + k].lower() == "active"]))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        self.t1 = time.perf_counter()
+        if self.how is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"], "samples": 0}
+        self.running = False
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         self.thread.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for k, nm in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower() == "active" for r in self.rows)]
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [r for r in self.rows if t0 <= r[0] <= self.t1]
+        where = "inside the timed region"
+        if not inside and self.rows:   # the sampler was slower than the region: the samples nearest to it (warm-up / just after)
+            inside = self.rows[-3:]
+            where = "nearest to the timed region (none fell inside)"
+        sm, mx = [r[1] for r in inside], [r[2] for r in inside]
+        reasons = sorted({nm for r in inside for nm in r[3]})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.how, "window": where}
 
 
 def cpu_oracle_rate(kind, seed, sample_n, threads, steps, warmup):
@@ -244,6 +297,7 @@ def run_native(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident steps
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started before the warm-up, counted from begin() on
     for _ in range(args.warmup):
         origin = con.bwt_device(d_text.data_ptr(), n, d_bwt.data_ptr())
     # B_alg of THIS block, measured on the GPU from the suffix array (dark_bwt_lcp_profile_device), outside the timed
@@ -256,11 +310,12 @@ def run_native(args, rank, local_rank, world):
         balg_live = prof["b_alg"] / n
         del d_sa
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     agg = {"pass_ms": 0.0, "gen_pass_ms": 0.0, "sorted": 0, "gen_sorted": 0, "passes": 0, "gen_passes": 0, "device_ms": 0.0, "init_ms": 0.0,
            "sort_ms": 0.0, "keybuild_ms": 0.0, "rerank_ms": 0.0, "emit_ms": 0.0, "host_syncs": 0}
+    if sampler:
+        sampler.begin()
     ev0.record(stream)
     for _ in range(args.steps):
         origin = con.bwt_device(d_text.data_ptr(), n, d_bwt.data_ptr())
