@@ -165,8 +165,9 @@ struct HostStage {
     static constexpr int kMaxLanes = 16;
     size_t chunk = 2u << 20;
     int lanes = 0;
-    u8* pinned = nullptr;
+    u8* pinned = nullptr;  // lanes x 2 slots x chunk
     cudaStream_t streams[kMaxLanes] = {nullptr};
+    cudaEvent_t slot_done[kMaxLanes][2] = {{nullptr}};  // the DMA out of / into a lane's slot has completed
 };
 
 struct dark_bwt_ctx {
@@ -1381,20 +1382,27 @@ int stage_prepare(dark_bwt_ctx* ctx, HostStage& st) {
     const int lanes = ctx->knobs.host_threads;
     if (lanes <= 0) return 1;  // staging switched off
     st.chunk = (size_t)ctx->knobs.host_chunk_mb << 20;
-    if (cudaHostAlloc((void**)&st.pinned, st.chunk * lanes, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc((void**)&st.pinned, st.chunk * lanes * 2, cudaHostAllocDefault) != cudaSuccess) {
         cudaGetLastError();
         st.pinned = nullptr;
         return 1;  // no pinned memory to be had: fall back to the driver's own staging
     }
-    for (int i = 0; i < lanes; ++i)
+    for (int i = 0; i < lanes; ++i) {
         if (cudaStreamCreateWithFlags(&st.streams[i], cudaStreamNonBlocking) != cudaSuccess) return ctx->fail_cuda(cudaGetLastError(), "staging stream", __LINE__);
+        for (int k = 0; k < 2; ++k)
+            if (cudaEventCreateWithFlags(&st.slot_done[i][k], cudaEventDisableTiming) != cudaSuccess)
+                return ctx->fail_cuda(cudaGetLastError(), "staging event", __LINE__);
+    }
     st.lanes = lanes;
     return 0;
 }
 
 void stage_release(HostStage& st) {
-    for (int i = 0; i < HostStage::kMaxLanes; ++i)
+    for (int i = 0; i < HostStage::kMaxLanes; ++i) {
         if (st.streams[i]) cudaStreamDestroy(st.streams[i]);
+        for (int k = 0; k < 2; ++k)
+            if (st.slot_done[i][k]) cudaEventDestroy(st.slot_done[i][k]);
+    }
     if (st.pinned) cudaFreeHost(st.pinned);
     st = HostStage();
 }
@@ -1412,20 +1420,39 @@ int staged_copy(dark_bwt_ctx* ctx, HostStage& st, void* dev, void* host, size_t 
             failed = 1;
             return;
         }
-        u8* slot = st.pinned + (size_t)lane * chunk;
+        // two pinned slots per lane: the memcpy of one chunk overlaps the DMA of the lane's other slot
+        u8* const slots[2] = {st.pinned + (size_t)(2 * lane) * chunk, st.pinned + (size_t)(2 * lane + 1) * chunk};
         cudaStream_t sm = st.streams[lane];
+        cudaEvent_t* done = st.slot_done[lane];
+        bool busy[2] = {false, false};            // H2D: a DMA out of the slot is in flight
+        size_t p_off = 0, p_len = 0;              // D2H: the chunk whose DMA into slot p_slot was issued last
+        int p_slot = -1, cur = 0;
+        auto ok = [&](cudaError_t e) {
+            if (e != cudaSuccess) failed = 1;
+            return e == cudaSuccess;
+        };
         for (;;) {
             const size_t c = next.fetch_add(1);
             if (c >= nchunks || failed.load()) break;
             const size_t off = c * chunk, len = std::min(chunk, bytes - off);
+            const int sl = cur;
+            cur ^= 1;
             if (to_device) {
-                memcpy(slot, (const u8*)host + off, len);
-                if (cudaMemcpyAsync((u8*)dev + off, slot, len, cudaMemcpyHostToDevice, sm) != cudaSuccess || cudaStreamSynchronize(sm) != cudaSuccess) failed = 1;
+                if (busy[sl] && !ok(cudaEventSynchronize(done[sl]))) break;
+                memcpy(slots[sl], (const u8*)host + off, len);
+                if (!ok(cudaMemcpyAsync((u8*)dev + off, slots[sl], len, cudaMemcpyHostToDevice, sm)) || !ok(cudaEventRecord(done[sl], sm))) break;
+                busy[sl] = true;
             } else {
-                if (cudaMemcpyAsync(slot, (const u8*)dev + off, len, cudaMemcpyDeviceToHost, sm) != cudaSuccess || cudaStreamSynchronize(sm) != cudaSuccess) failed = 1;
-                else memcpy((u8*)host + off, slot, len);
+                if (!ok(cudaMemcpyAsync(slots[sl], (const u8*)dev + off, len, cudaMemcpyDeviceToHost, sm)) || !ok(cudaEventRecord(done[sl], sm))) break;
+                if (p_slot >= 0) {
+                    if (!ok(cudaEventSynchronize(done[p_slot]))) break;
+                    memcpy((u8*)host + p_off, slots[p_slot], p_len);
+                }
+                p_slot = sl, p_off = off, p_len = len;
             }
         }
+        if (!to_device && p_slot >= 0 && !failed.load() && ok(cudaEventSynchronize(done[p_slot]))) memcpy((u8*)host + p_off, slots[p_slot], p_len);
+        ok(cudaStreamSynchronize(sm));
     };
     std::vector<std::thread> pool;
     for (int i = 1; i < lanes; ++i) pool.emplace_back(work, i);

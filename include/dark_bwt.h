@@ -100,7 +100,7 @@ typedef struct dark_bwt_stats {
 /* Constructor::new — allocates every device buffer for blocks of up to max_n bytes on
  * CUDA device `device`: one arena of 45 * max_n bytes of HBM (41 * max_n with DARK_BWT_F_DEVICE_ONLY; 11.2 GiB for a
  * 256 MiB block, 89.8 GiB for 2 GiB).  No device memory is allocated later; the pinned staging lanes for pageable host
- * buffers (12 lanes x 2 MiB per direction) and the `reuse` scratch are allocated by the first call that needs them. */
+ * buffers (12 lanes x 2 slots x 2 MiB per direction) and the `reuse` scratch are allocated by the first call that needs them. */
 int dark_bwt_create(uint64_t max_n, int device, dark_bwt_ctx **out);
 int dark_bwt_create_ex(uint64_t max_n, int device, uint32_t flags, dark_bwt_ctx **out);
 
